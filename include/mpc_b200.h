@@ -1,0 +1,153 @@
+/*
+ * mpc_b200.h — C-ABI of the B200-native batched convex-MPC stance-force solver.
+ *
+ * This is the drop-in boundary for the reference's native QP path:
+ *   reference/MPC_Controller/convex_MPC/mpc_osqp.cc:178-279  class ConvexMpc
+ *   reference/MPC_Controller/convex_MPC/mpc_osqp.cc:578-591  ComputeContactForces(13 args)
+ *   reference/MPC_Controller/convex_MPC/mpc_osqp.cc:952-983  PYBIND11_MODULE(mpc_osqp)
+ * and (batched extension, no reference counterpart) for the per-robot loop in
+ *   reference/RL_Environment/tasks/aliengo.py:227-263        pre_physics_step
+ *
+ * Everything here is plain C: device/host pointers, sizes, an opaque stream.
+ * No torch types.  All entry points return 0 on success or a negative
+ * MPC_B200_E* code; none of them synchronises the device unless documented.
+ *
+ * ---- problem record (one per robot, float32, AoS so that one warp pulls one
+ * robot's whole state block with a single TMA bulk copy) --------------------
+ * The fields are exactly the 13 arguments of ConvexMpc::ComputeContactForces
+ * (mpc_osqp.cc:578-591), in the reference's argument order, followed by the
+ * flattened horizon contact table (index i*4+leg, mpc_osqp.cc:598-601).
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* float offsets inside one problem record */
+#define MPC_REC_WEIGHTS      0   /* 13  qp_weights                      */
+#define MPC_REC_COM_POS     13   /*  3  com_position                    */
+#define MPC_REC_COM_VEL     16   /*  3  com_velocity                    */
+#define MPC_REC_RPY         19   /*  3  com_roll_pitch_yaw              */
+#define MPC_REC_NORMAL      22   /*  3  ground_normal_vec               */
+#define MPC_REC_ANGVEL      25   /*  3  com_angular_velocity            */
+#define MPC_REC_FOOTPOS     28   /* 12  foot_positions_body_frame       */
+#define MPC_REC_MU          40   /*  4  foot_friction_coeffs            */
+#define MPC_REC_DES_POS     44   /*  3  desired_com_position            */
+#define MPC_REC_DES_VEL     47   /*  3  desired_com_velocity            */
+#define MPC_REC_DES_RPY     50   /*  3  desired_com_roll_pitch_yaw      */
+#define MPC_REC_DES_ANGVEL  53   /*  3  desired_com_angular_velocity    */
+#define MPC_REC_CONTACT     56   /* 4*h foot_contact_states (0/1)       */
+/* record stride in floats: 56 + 4*h rounded up to a multiple of 4 (16 B)  */
+#define MPC_REC_STRIDE(h)   ((56 + 4 * (h) + 3) & ~3)
+
+/* per-robot-type constant block (float32): what ConvexMpc's ctor receives
+ * (mpc_osqp.cc:508-527): mass, inertia[9] row-major, then 2 pad floats.     */
+#define MPC_ROBOT_PARAMS_STRIDE 12
+
+#define MPC_B200_MAX_HORIZON 16
+
+/* error codes */
+#define MPC_B200_OK            0
+#define MPC_B200_EINVAL       -1   /* bad argument (null ptr, horizon, ...)  */
+#define MPC_B200_ECUDA        -2   /* CUDA runtime error (see last_error)    */
+#define MPC_B200_ENOGPU       -3   /* no CUDA device: there is NO CPU path   */
+#define MPC_B200_ESMEM        -4   /* problem does not fit in shared memory  */
+
+/* per-robot status written by the kernel (int32) */
+#define MPC_STATUS_SOLVED          1   /* mirrors OSQP_SOLVED (constants.h)   */
+#define MPC_STATUS_MAX_ITER       -2   /* fixed iterations ended above tol    */
+#define MPC_STATUS_NON_FINITE     -7   /* NaN/Inf met -> forces zeroed        */
+
+/* Solver settings.  Defaults (mpc_b200_default_settings) reproduce the
+ * reference's *answer* (the unique minimiser OSQP+polish returns,
+ * mpc_osqp.cc:705-712), not OSQP's iteration count.                         */
+typedef struct MpcB200Settings {
+  int   horizon;        /* planning_horizon (mpc_osqp.cc:511), <= 16          */
+  int   admm_iters;     /* fixed ADMM iteration count                         */
+  int   polish;         /* 1: active-set polish after ADMM (osqp polish.c)    */
+  int   warm_start;     /* 1: start from caller-provided x/y state buffers    */
+  float dt;             /* timestep (mpc_osqp.cc:512), MPC dt = 0.02          */
+  float alpha;          /* force regulariser (mpc_osqp.cc:513), 1e-5          */
+  float rho;            /* ADMM penalty on the un-scaled problem              */
+  float sigma;          /* ADMM prox weight (osqp constants.h SIGMA = 1e-6)   */
+  float relax;          /* over-relaxation (osqp constants.h ALPHA = 1.6)     */
+  float eps_abs;        /* status threshold on the final residuals            */
+  float eps_rel;
+  int   reserved[5];
+} MpcB200Settings;
+
+void mpc_b200_default_settings(MpcB200Settings* s);
+
+/* library / device probes (host only, never touch the GPU context lazily) */
+const char* mpc_b200_version(void);
+const char* mpc_b200_last_error(void);
+int  mpc_b200_device_count(void);
+
+/* Bytes of dynamic shared memory one CTA of the solve kernel needs for the
+ * given horizon, and the number of robots (warps) per CTA it was built for. */
+int  mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta,
+                          int* regs_per_thread);
+
+/*
+ * Batched solve: n_robots independent QPs, one warp per robot.
+ *   d_records      [n_robots, MPC_REC_STRIDE(h)] float32, device
+ *   d_robot_params [n_types, MPC_ROBOT_PARAMS_STRIDE] float32, device
+ *   d_robot_type   [n_robots] int32 device, or NULL (all robots type 0)
+ *   d_grf0         [n_robots, 12] float32 device: horizon-0 contact forces,
+ *                  NEGATED QP solution exactly as mpc_osqp.cc:789-790 returns
+ *   d_grf_full     [n_robots, 12*h] float32 device or NULL (full horizon)
+ *   d_status       [n_robots] int32 device or NULL
+ *   d_resid        [n_robots, 2] float32 device or NULL (primal, dual residual)
+ *   d_warm         [n_robots, 32*h] float32 device or NULL: ADMM state
+ *                  (x[12h], y[20h]) read when settings->warm_start, always
+ *                  written when non-NULL
+ *   stream         cudaStream_t as void* (NULL = legacy default stream)
+ * Asynchronous w.r.t. the host.
+ */
+int mpc_b200_solve_batch(const MpcB200Settings* settings,
+                         const float* d_records,
+                         const float* d_robot_params,
+                         const int32_t* d_robot_type,
+                         int n_robots,
+                         float* d_grf0,
+                         float* d_grf_full,
+                         int32_t* d_status,
+                         float* d_resid,
+                         float* d_warm,
+                         void* stream);
+
+/*
+ * Host-buffer convenience used by the ConvexMpc compatibility class and the
+ * e2e benchmark leg: copies records H2D, solves, copies forces D2H on an
+ * internal stream and synchronises.  Same argument meaning as above but all
+ * pointers are HOST pointers (pinned or pageable).
+ */
+int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
+                              const float* h_records,
+                              const float* h_robot_params,
+                              const int32_t* h_robot_type,
+                              int n_robots,
+                              float* h_grf0,
+                              float* h_grf_full,
+                              int32_t* h_status);
+
+/* Debug / test hook: build the dense QP (P[n*n] row-major, q[n], C rows as
+ * 5x3 blocks [4h*15], l[20h], u[20h]; doubles, n = 12h) for ONE record on
+ * the device with the same code the solve kernel uses, and copy it to host.
+ * Used by the parity tests to compare the on-device builder with the oracle
+ * builder entry by entry.                                                   */
+int mpc_b200_debug_build_qp(const MpcB200Settings* settings,
+                            const float* h_record,
+                            const float* h_robot_params,
+                            double* h_P, double* h_q,
+                            double* h_C, double* h_l, double* h_u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */
