@@ -60,25 +60,39 @@ extern "C" {
 
 /* per-robot status written by the kernel (int32) */
 #define MPC_STATUS_SOLVED          1   /* mirrors OSQP_SOLVED (constants.h)   */
-#define MPC_STATUS_MAX_ITER       -2   /* fixed iterations ended above tol    */
+#define MPC_STATUS_MAX_ITER       -2   /* mirrors OSQP_MAX_ITER_REACHED       */
 #define MPC_STATUS_NON_FINITE     -7   /* NaN/Inf met -> forces zeroed        */
 
-/* Solver settings.  Defaults (mpc_b200_default_settings) reproduce the
- * reference's *answer* (the unique minimiser OSQP+polish returns,
- * mpc_osqp.cc:705-712), not OSQP's iteration count.                         */
+/* Solver modes */
+#define MPC_MODE_OSQP   0  /* reproduce the reference's OSQP run step for step (fp64): Ruiz
+                              scaling, adaptive rho, termination every 25 its, polish.  This
+                              is what mpc_osqp.cc:690-796 returns on the same inputs.        */
+#define MPC_MODE_FIXED  1  /* same iteration, but exactly `admm_iters` ADMM iterations and no
+                              termination test / rho adaptation (BASELINE config 5 sweeps)   */
+
+/* Solver settings.  mpc_b200_default_settings() gives the reference configuration
+ * (osqp include/constants.h:59-110 overridden by mpc_osqp.cc:705-712).            */
 typedef struct MpcB200Settings {
-  int   horizon;        /* planning_horizon (mpc_osqp.cc:511), <= 16          */
-  int   admm_iters;     /* fixed ADMM iteration count                         */
-  int   polish;         /* 1: active-set polish after ADMM (osqp polish.c)    */
-  int   warm_start;     /* 1: start from caller-provided x/y state buffers    */
-  float dt;             /* timestep (mpc_osqp.cc:512), MPC dt = 0.02          */
-  float alpha;          /* force regulariser (mpc_osqp.cc:513), 1e-5          */
-  float rho;            /* ADMM penalty on the un-scaled problem              */
-  float sigma;          /* ADMM prox weight (osqp constants.h SIGMA = 1e-6)   */
-  float relax;          /* over-relaxation (osqp constants.h ALPHA = 1.6)     */
-  float eps_abs;        /* status threshold on the final residuals            */
-  float eps_rel;
-  int   reserved[5];
+  int   horizon;        /* planning_horizon (mpc_osqp.cc:511): 10 or 16             */
+  int   mode;           /* MPC_MODE_*                                                */
+  int   admm_iters;     /* MPC_MODE_FIXED: iteration count                           */
+  int   max_iter;       /* MPC_MODE_OSQP: osqp MAX_ITER (4000)                       */
+  int   check_every;    /* osqp CHECK_TERMINATION == adaptive_rho_interval (25)      */
+  int   scaling_iters;  /* osqp SCALING (10)                                         */
+  int   adaptive_rho;   /* osqp ADAPTIVE_RHO (1)                                     */
+  int   polish;         /* mpc_osqp.cc:709 (1)                                       */
+  int   polish_refine;  /* osqp POLISH_REFINE_ITER (3)                               */
+  int   reserved_i[3];
+  double dt;            /* timestep (mpc_osqp.cc:512), MPC dt = 0.02                 */
+  double alpha;         /* force regulariser (mpc_osqp.cc:513), 1e-5                 */
+  double rho;           /* osqp RHO 0.1                                              */
+  double sigma;         /* osqp SIGMA 1e-6                                           */
+  double relax;         /* osqp ALPHA 1.6                                            */
+  double eps_abs;       /* mpc_osqp.cc:711  1e-3                                     */
+  double eps_rel;       /* mpc_osqp.cc:712  1e-3                                     */
+  double delta;         /* osqp DELTA 1e-6 (polish regularisation)                   */
+  double rho_tol_ratio; /* osqp ADAPTIVE_RHO_TOLERANCE 5                             */
+  double reserved_d[3];
 } MpcB200Settings;
 
 void mpc_b200_default_settings(MpcB200Settings* s);
@@ -103,9 +117,8 @@ int  mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta,
  *   d_grf_full     [n_robots, 12*h] float32 device or NULL (full horizon)
  *   d_status       [n_robots] int32 device or NULL
  *   d_resid        [n_robots, 2] float32 device or NULL (primal, dual residual)
- *   d_warm         [n_robots, 32*h] float32 device or NULL: ADMM state
- *                  (x[12h], y[20h]) read when settings->warm_start, always
- *                  written when non-NULL
+ *   d_info         [n_robots, 8] float64 device or NULL: iterations, rho updates,
+ *                  final rho, polish status, pri_res, dua_res, cost scale, n_free
  *   stream         cudaStream_t as void* (NULL = legacy default stream)
  * Asynchronous w.r.t. the host.
  */
@@ -118,7 +131,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings,
                          float* d_grf_full,
                          int32_t* d_status,
                          float* d_resid,
-                         float* d_warm,
+                         double* d_info,
                          void* stream);
 
 /*
@@ -136,16 +149,18 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
                               float* h_grf_full,
                               int32_t* h_status);
 
-/* Debug / test hook: build the dense QP (P[n*n] row-major, q[n], C rows as
- * 5x3 blocks [4h*15], l[20h], u[20h]; doubles, n = 12h) for ONE record on
- * the device with the same code the solve kernel uses, and copy it to host.
- * Used by the parity tests to compare the on-device builder with the oracle
- * builder entry by entry.                                                   */
+/* Debug / test hook: run ONE record through the solve kernel and copy back the
+ * quantities the kernel never materialises in production: the dense Hessian
+ * P[n*n] (row-major, n = 12h) and gradient q[n] of the condensed QP
+ * (mpc_osqp.cc:678-683) evaluated from the on-chip closed form, and OSQP's
+ * Ruiz scaling D[n], E[20h], c.  Used by the parity tests to compare the
+ * on-device builder with the oracle builder entry by entry.  Host pointers;
+ * synchronises.                                                             */
 int mpc_b200_debug_build_qp(const MpcB200Settings* settings,
                             const float* h_record,
                             const float* h_robot_params,
                             double* h_P, double* h_q,
-                            double* h_C, double* h_l, double* h_u);
+                            double* h_D, double* h_E, double* h_c);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,85 @@
+"""ctypes binding of the C-ABI library ``libmpc_b200.so`` (include/mpc_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+CPU fallback: if the shared object is missing, or no CUDA device is visible, every solve
+raises :class:`MpcB200Error`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+
+MODE_OSQP, MODE_FIXED = 0, 1
+STATUS_SOLVED, STATUS_MAX_ITER = 1, -2
+EXPORTS = ("mpc_b200_default_settings", "mpc_b200_version", "mpc_b200_last_error",
+           "mpc_b200_device_count", "mpc_b200_kernel_info", "mpc_b200_solve_batch",
+           "mpc_b200_solve_batch_host", "mpc_b200_debug_build_qp")
+
+
+class MpcB200Error(RuntimeError):
+    pass
+
+
+class Settings(C.Structure):
+    """Mirror of ``MpcB200Settings`` (include/mpc_b200.h)."""
+    _fields_ = [("horizon", C.c_int), ("mode", C.c_int), ("admm_iters", C.c_int), ("max_iter", C.c_int),
+                ("check_every", C.c_int), ("scaling_iters", C.c_int), ("adaptive_rho", C.c_int),
+                ("polish", C.c_int), ("polish_refine", C.c_int), ("reserved_i", C.c_int * 3),
+                ("dt", C.c_double), ("alpha", C.c_double), ("rho", C.c_double), ("sigma", C.c_double),
+                ("relax", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+                ("delta", C.c_double), ("rho_tol_ratio", C.c_double), ("reserved_d", C.c_double * 3)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (once).  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MpcB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.mpc_b200_default_settings.argtypes = [C.POINTER(Settings)]
+        L.mpc_b200_default_settings.restype = None
+        L.mpc_b200_version.restype = C.c_char_p
+        L.mpc_b200_last_error.restype = C.c_char_p
+        L.mpc_b200_device_count.restype = C.c_int
+        L.mpc_b200_kernel_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.mpc_b200_kernel_info.restype = C.c_int
+        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_solve_batch.restype = C.c_int
+        L.mpc_b200_solve_batch_host.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp]
+        L.mpc_b200_solve_batch_host.restype = C.c_int
+        L.mpc_b200_debug_build_qp.argtypes = [C.POINTER(Settings), vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_debug_build_qp.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def default_settings(**overrides) -> Settings:
+    s = Settings()
+    lib().mpc_b200_default_settings(C.byref(s))
+    for k, v in overrides.items():
+        if not hasattr(s, k):
+            raise AttributeError(f"MpcB200Settings has no field {k!r}")
+        setattr(s, k, v)
+    return s
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().mpc_b200_last_error().decode()
+        raise MpcB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def kernel_info(horizon: int) -> dict:
+    smem, rpc, regs = C.c_int(), C.c_int(), C.c_int()
+    check(lib().mpc_b200_kernel_info(horizon, C.byref(smem), C.byref(rpc), C.byref(regs)), "kernel_info")
+    return {"smem_bytes": smem.value, "robots_per_cta": rpc.value, "regs_per_thread": regs.value}

@@ -1,0 +1,366 @@
+// mpc_b200.cu — sm_100a kernels + the C-ABI of include/mpc_b200.h.
+//
+// One CTA = one warp = one robot.  The hardware block scheduler load-balances the
+// variable per-robot iteration counts (OSQP terminates after 50..300 iterations depending
+// on the state).  The robot's 384-byte problem record is staged HBM -> shared memory with
+// one TMA bulk copy (cp.async.bulk, mbarrier completion); everything else the solver
+// touches lives in registers / shared memory until the 12 horizon-0 forces are written.
+//
+// There is NO CPU fallback in this library: without a CUDA device every entry point
+// returns MPC_B200_ENOGPU.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/mpc_b200.h"
+#include "mpc_warp_solver.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return MPC_B200_ECUDA;
+}
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+// ---------------------------------------------------------------- TMA bulk copy helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int H>
+struct KernelCfg {
+  using D = mpc::Dims<H>;
+  static constexpr int REC_FLOATS = MPC_REC_STRIDE(H);
+  static constexpr int REC_BYTES = REC_FLOATS * 4;
+  // [solver doubles][record floats (16B aligned)][robot params 12 floats][mbarrier]
+  static constexpr int OFF_REC = D::SMEM_DOUBLES * 8;
+  static constexpr int OFF_RP = OFF_REC + ((REC_BYTES + 15) & ~15);
+  static constexpr int OFF_BAR = OFF_RP + 64;
+  static constexpr int SMEM_BYTES = OFF_BAR + 16;
+};
+
+template <int H>
+__global__ void __launch_bounds__(32, 1)
+mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
+                 const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
+                 int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
+                 int32_t* __restrict__ status, float* __restrict__ resid, double* __restrict__ info,
+                 double* __restrict__ dbg) {
+  using K = KernelCfg<H>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  float* rec_s = reinterpret_cast<float*>(smem_raw + K::OFF_REC);
+  float* rp_s = reinterpret_cast<float*>(smem_raw + K::OFF_RP);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);
+  const int lane = threadIdx.x;
+  const int robot = blockIdx.x;
+  if (robot >= n_robots) return;
+
+  // stage the robot's state block with one TMA bulk copy while the tables are built
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_load_1d(rec_s, records + (size_t)robot * K::REC_FLOATS, K::REC_BYTES, bar);
+  }
+  const int type = robot_type ? robot_type[robot] : 0;
+  if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
+  mpc::fill_tables<H>(sm, prm.dt, lane);
+  __syncwarp();
+  mbar_wait(bar, 0);
+
+  constexpr int dbg_stride = 12 * H + 144 * H * H + 12 * H + 20 * H + 1;
+  mpc::solve_robot<H>(rec_s, rp_s, prm, sm, grf0 + (size_t)robot * 12,
+                      grf_full ? grf_full + (size_t)robot * 12 * H : nullptr,
+                      status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
+                      info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr,
+                      dbg ? dbg + (size_t)robot * dbg_stride : nullptr, lane);
+}
+
+mpc::SolveParams to_params(const MpcB200Settings& s) {
+  mpc::SolveParams p;
+  memset(&p, 0, sizeof(p));
+  p.max_iter = s.max_iter;
+  p.check_every = s.check_every;
+  p.scaling_iters = s.scaling_iters;
+  p.polish = s.polish;
+  p.polish_refine = s.polish_refine;
+  p.adaptive_rho = (s.mode == MPC_MODE_FIXED) ? 0 : s.adaptive_rho;
+  p.fixed_iters = (s.mode == MPC_MODE_FIXED) ? s.admm_iters : 0;
+  p.dt = s.dt;
+  p.alpha = s.alpha;
+  p.rho0 = s.rho;
+  p.sigma = s.sigma;
+  p.relax = s.relax;
+  p.eps_abs = s.eps_abs;
+  p.eps_rel = s.eps_rel;
+  p.delta = s.delta;
+  p.rho_tol_ratio = s.rho_tol_ratio;
+  return p;
+}
+
+int check_settings(const MpcB200Settings* s) {
+  if (!s) {
+    snprintf(g_err, sizeof(g_err), "settings is NULL");
+    return MPC_B200_EINVAL;
+  }
+  if (s->horizon != 10 && s->horizon != 16) {
+    snprintf(g_err, sizeof(g_err), "horizon %d not built (supported: 10, 16)", s->horizon);
+    return MPC_B200_EINVAL;
+  }
+  if (s->mode == MPC_MODE_FIXED && s->admm_iters <= 0) {
+    snprintf(g_err, sizeof(g_err), "MPC_MODE_FIXED needs admm_iters > 0");
+    return MPC_B200_EINVAL;
+  }
+  if (s->mode != MPC_MODE_FIXED && s->mode != MPC_MODE_OSQP) {
+    snprintf(g_err, sizeof(g_err), "unknown mode %d", s->mode);
+    return MPC_B200_EINVAL;
+  }
+  if (s->check_every <= 0 || s->max_iter <= 0 || !(s->dt > 0) || !(s->rho > 0)) {
+    snprintf(g_err, sizeof(g_err), "invalid settings (check_every/max_iter/dt/rho must be > 0)");
+    return MPC_B200_EINVAL;
+  }
+  return MPC_B200_OK;
+}
+
+template <int H>
+int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n,
+           float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg,
+           cudaStream_t stream) {
+  using K = KernelCfg<H>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    K::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
+  if (n <= 0) return MPC_B200_OK;
+  mpc_solve_kernel<H><<<n, 32, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status, resid,
+                                                       info, dbg);
+  CK(cudaGetLastError());
+  return MPC_B200_OK;
+}
+
+int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int n,
+             float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg,
+             cudaStream_t stream) {
+  const mpc::SolveParams prm = to_params(*s);
+  if (s->horizon == 10) return launch<10>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, stream);
+  return launch<16>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, stream);
+}
+
+// grow-only device scratch for the host-pointer convenience entry points
+struct HostPath {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  void* buf = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (!stream) CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (bytes > cap) {
+      if (buf) cudaFree(buf);
+      buf = nullptr;
+      cap = 0;
+      CK(cudaMalloc(&buf, bytes));
+      cap = bytes;
+    }
+    return MPC_B200_OK;
+  }
+} g_host;
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+void mpc_b200_default_settings(MpcB200Settings* s) {
+  memset(s, 0, sizeof(*s));
+  s->horizon = 10;              // ConvexMPCLocomotion.py:27
+  s->mode = MPC_MODE_OSQP;
+  s->admm_iters = 50;
+  s->max_iter = 4000;           // osqp constants.h:61
+  s->check_every = 25;          // constants.h:83, mpc_osqp.cc:710
+  s->scaling_iters = 10;        // constants.h:85
+  s->adaptive_rho = 1;          // constants.h:105
+  s->polish = 1;                // mpc_osqp.cc:709
+  s->polish_refine = 3;         // constants.h:78
+  s->dt = 0.02;                 // RobotRunnerMin.py:21-22 (dtMPC = 0.01 * 2)
+  s->alpha = 1e-5;              // Parameters.py:6
+  s->rho = 0.1;                 // constants.h:59
+  s->sigma = 1e-6;              // constants.h:60
+  s->relax = 1.6;               // constants.h:66
+  s->eps_abs = 1e-3;            // mpc_osqp.cc:711
+  s->eps_rel = 1e-3;            // mpc_osqp.cc:712
+  s->delta = 1e-6;              // constants.h:76
+  s->rho_tol_ratio = 5.0;       // constants.h:110
+}
+
+const char* mpc_b200_version(void) { return "rl_mpc_locomotion_b200 0.1.0 (sm_100a)"; }
+const char* mpc_b200_last_error(void) { return g_err; }
+
+int mpc_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int* regs_per_thread) {
+  if (horizon != 10 && horizon != 16) return MPC_B200_EINVAL;
+  if (smem_bytes) *smem_bytes = horizon == 10 ? KernelCfg<10>::SMEM_BYTES : KernelCfg<16>::SMEM_BYTES;
+  if (robots_per_cta) *robots_per_cta = 1;
+  if (regs_per_thread) {
+    *regs_per_thread = -1;
+    cudaFuncAttributes a;
+    cudaError_t e = horizon == 10 ? cudaFuncGetAttributes(&a, mpc_solve_kernel<10>)
+                                  : cudaFuncGetAttributes(&a, mpc_solve_kernel<16>);
+    if (e == cudaSuccess) *regs_per_thread = a.numRegs;
+    else cudaGetLastError();
+  }
+  return MPC_B200_OK;
+}
+
+int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records,
+                         const float* d_robot_params, const int32_t* d_robot_type, int n_robots,
+                         float* d_grf0, float* d_grf_full, int32_t* d_status, float* d_resid,
+                         double* d_info, void* stream) {
+  int rc = check_settings(settings);
+  if (rc) return rc;
+  if (!d_records || !d_robot_params || !d_grf0 || n_robots < 0) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+    return MPC_B200_EINVAL;
+  }
+  if (mpc_b200_device_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
+    return MPC_B200_ENOGPU;
+  }
+  return dispatch(settings, d_records, d_robot_params, d_robot_type, n_robots, d_grf0, d_grf_full, d_status,
+                  d_resid, d_info, nullptr, (cudaStream_t)stream);
+}
+
+int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_records,
+                              const float* h_robot_params, const int32_t* h_robot_type, int n_robots,
+                              float* h_grf0, float* h_grf_full, int32_t* h_status) {
+  int rc = check_settings(settings);
+  if (rc) return rc;
+  if (!h_records || !h_robot_params || !h_grf0 || n_robots < 0) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+    return MPC_B200_EINVAL;
+  }
+  if (mpc_b200_device_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
+    return MPC_B200_ENOGPU;
+  }
+  if (n_robots == 0) return MPC_B200_OK;
+  const int h = settings->horizon;
+  int n_types = 1;
+  if (h_robot_type)
+    for (int i = 0; i < n_robots; ++i) n_types = h_robot_type[i] + 1 > n_types ? h_robot_type[i] + 1 : n_types;
+  const size_t b_rec = align256((size_t)n_robots * MPC_REC_STRIDE(h) * 4);
+  const size_t b_rp = align256((size_t)n_types * MPC_ROBOT_PARAMS_STRIDE * 4);
+  const size_t b_rt = align256((size_t)n_robots * 4);
+  const size_t b_g0 = align256((size_t)n_robots * 12 * 4);
+  const size_t b_gf = align256((size_t)n_robots * 12 * h * 4);
+  const size_t b_st = align256((size_t)n_robots * 4);
+  std::lock_guard<std::mutex> lock(g_host.mu);
+  rc = g_host.ensure(b_rec + b_rp + b_rt + b_g0 + b_gf + b_st);
+  if (rc) return rc;
+  char* p = (char*)g_host.buf;
+  float* d_rec = (float*)p; p += b_rec;
+  float* d_rp = (float*)p; p += b_rp;
+  int32_t* d_rt = (int32_t*)p; p += b_rt;
+  float* d_g0 = (float*)p; p += b_g0;
+  float* d_gf = (float*)p; p += b_gf;
+  int32_t* d_st = (int32_t*)p;
+  cudaStream_t st = g_host.stream;
+  CK(cudaMemcpyAsync(d_rec, h_records, (size_t)n_robots * MPC_REC_STRIDE(h) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_rp, h_robot_params, (size_t)n_types * MPC_ROBOT_PARAMS_STRIDE * 4,
+                     cudaMemcpyHostToDevice, st));
+  if (h_robot_type) CK(cudaMemcpyAsync(d_rt, h_robot_type, (size_t)n_robots * 4, cudaMemcpyHostToDevice, st));
+  rc = dispatch(settings, d_rec, d_rp, h_robot_type ? d_rt : nullptr, n_robots, d_g0,
+                h_grf_full ? d_gf : nullptr, h_status ? d_st : nullptr, nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_grf0, d_g0, (size_t)n_robots * 12 * 4, cudaMemcpyDeviceToHost, st));
+  if (h_grf_full) CK(cudaMemcpyAsync(h_grf_full, d_gf, (size_t)n_robots * 12 * h * 4, cudaMemcpyDeviceToHost, st));
+  if (h_status) CK(cudaMemcpyAsync(h_status, d_st, (size_t)n_robots * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPC_B200_OK;
+}
+
+int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_record,
+                            const float* h_robot_params, double* h_P, double* h_q, double* h_D,
+                            double* h_E, double* h_c) {
+  int rc = check_settings(settings);
+  if (rc) return rc;
+  if (mpc_b200_device_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
+    return MPC_B200_ENOGPU;
+  }
+  const int h = settings->horizon, nv = 12 * h;
+  const size_t ndbg = (size_t)nv + (size_t)nv * nv + nv + 20 * h + 1;
+  float *d_rec = nullptr, *d_rp = nullptr, *d_g0 = nullptr;
+  double* d_dbg = nullptr;
+  CK(cudaMalloc(&d_rec, MPC_REC_STRIDE(h) * 4));
+  CK(cudaMalloc(&d_rp, MPC_ROBOT_PARAMS_STRIDE * 4));
+  CK(cudaMalloc(&d_g0, 12 * 4));
+  CK(cudaMalloc(&d_dbg, ndbg * 8));
+  CK(cudaMemcpy(d_rec, h_record, MPC_REC_STRIDE(h) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_rp, h_robot_params, MPC_ROBOT_PARAMS_STRIDE * 4, cudaMemcpyHostToDevice));
+  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr);
+  if (rc == MPC_B200_OK) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = cuda_fail(e, "debug kernel");
+  }
+  if (rc == MPC_B200_OK) {
+    if (h_q) cudaMemcpy(h_q, d_dbg, nv * 8, cudaMemcpyDeviceToHost);
+    if (h_P) cudaMemcpy(h_P, d_dbg + nv, (size_t)nv * nv * 8, cudaMemcpyDeviceToHost);
+    if (h_D) cudaMemcpy(h_D, d_dbg + nv + (size_t)nv * nv, nv * 8, cudaMemcpyDeviceToHost);
+    if (h_E) cudaMemcpy(h_E, d_dbg + nv + (size_t)nv * nv + nv, 20 * h * 8, cudaMemcpyDeviceToHost);
+    if (h_c) cudaMemcpy(h_c, d_dbg + ndbg - 1, 8, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_rec);
+  cudaFree(d_rp);
+  cudaFree(d_g0);
+  cudaFree(d_dbg);
+  return rc;
+}
+
+}  // extern "C"

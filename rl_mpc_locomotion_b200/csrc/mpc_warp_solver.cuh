@@ -1,0 +1,1512 @@
+// mpc_warp_solver.cuh — one warp owns one robot's stance-force QP end to end.
+//
+// What it computes (reference file:line it replaces):
+//   * the condensed single-rigid-body QP of ConvexMpc::ComputeContactForces
+//     (reference/MPC_Controller/convex_MPC/mpc_osqp.cc:593-692) — built on chip from the
+//     96-float problem record, never materialised (see "QP structure" below);
+//   * OSQP 0.6.0 exactly as the reference drives it (mpc_osqp.cc:705-712, :757-796 and
+//     reference/extern/osqp/src/{osqp.c:288-630, auxil.c, scaling.c, polish.c}): Ruiz
+//     equilibration (10 passes), rho vector with 1e3*rho on equality rows, ADMM with
+//     alpha=1.6 / sigma=1e-6, residual check + rho adaptation every 25 iterations,
+//     eps_abs=eps_rel=1e-3, polish (delta=1e-6, 3 refinement steps), unscale, negate.
+//   The reference's loosely converged output depends on that whole trajectory (the true
+//   minimiser is up to ~100 N away on the benchmark distribution), so reproducing the
+//   *algorithm* in fp64 is the only way to return what the reference returns.
+//
+// QP structure: with E = [I_w^-1 [r_i]x ; I/m] (6x12, "wrench map"),
+//   P = alpha*I + 2 (I_h (x) E)^T (Gamma (x) Q1 + N (x) Q2) (I_h (x) E),
+//   Gamma_ij = sum_{k>=max(i,j)} c_{k-i} c_{k-j}, c_m = dt^2 (m + 1/2), N_ij = h - max(i,j),
+//   Q1 = blkdiag(T^T W_rpy T, W_pos), Q2 = dt^2 blkdiag(W_omega, W_vel),
+// and the friction constraints are 5x3 blocks per (step, leg).  Hence the ADMM matrix
+//   K = Pbar + sigma*I + Abar^T diag(rho) Abar = Delta + U^T Q U
+// is "3x3-block-diagonal + rank 6h", and K^-1 is applied through the 6h x 6h SPD matrix
+//   Hm = blkdiag(F_k^-1) + Q,  F_k = U_k Delta_k^-1 U_k^T            (Woodbury)
+// whose Cholesky factor is inverted once per factorisation so that every ADMM iteration
+// is two conflict-free triangular mat-vecs out of shared memory (no dependent chain).
+//
+// Written in the warp-program dialect of warp_prog.h: compiles for sm_100a (product) and,
+// with -DMPC_EMULATE, as a sequential 32-lane emulation for GPU-less CI.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/mpc_b200.h"
+#include "warp_prog.h"
+
+namespace mpc {
+
+struct SolveParams {
+  int max_iter;         // osqp MAX_ITER 4000
+  int check_every;      // osqp CHECK_TERMINATION 25 (== adaptive_rho_interval, mpc_osqp.cc:710)
+  int scaling_iters;    // osqp SCALING 10
+  int polish;           // mpc_osqp.cc:709
+  int polish_refine;    // osqp POLISH_REFINE_ITER 3
+  int adaptive_rho;     // osqp ADAPTIVE_RHO 1
+  int fixed_iters;      // >0: run exactly this many iterations, no termination test
+  int reserved;
+  double dt, alpha;     // mpc_osqp.cc:512-513
+  double rho0, sigma, relax, eps_abs, eps_rel, delta, rho_tol_ratio;
+};
+
+// per-robot diagnostic record (doubles) written when d_info != nullptr
+enum { INFO_ITERS = 0, INFO_RHO_UPDATES, INFO_RHO, INFO_POLISH, INFO_PRI, INFO_DUA,
+       INFO_C, INFO_NFREE, INFO_STRIDE = 8 };
+
+constexpr double kGravity = 9.8;    // mpc_osqp.cc:54
+constexpr double kMaxScale = 10.0;  // mpc_osqp.cc:55
+constexpr double kMinScale = 0.1;   // mpc_osqp.cc:56
+constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqFactor = 1e3, kRhoTol = 1e-4;
+constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
+
+template <int H>
+struct Dims {
+  static constexpr int NV = 12 * H;             // variables
+  static constexpr int NLS = 4 * H;             // (step, leg) pairs
+  static constexpr int NSLOT = (NLS + 31) / 32; // leg-steps per lane
+  static constexpr int NW = 6 * H;              // wrench-space dimension
+  static constexpr int NWP = NW + 1;            // padded column stride (bank-conflict free)
+  static constexpr int NWS = (NW + 31) / 32;
+  static constexpr int NVS = (NV + 31) / 32;
+  // shared-memory layout (doubles)
+  static constexpr int OFF_WM = 0;                       // [NW][NWP] Hm -> L (lower) / W^T (upper)
+  static constexpr int OFF_SCR = OFF_WM + NW * NWP;      // scratch: vecA vecB vt vg vw Finv
+  static constexpr int OFF_VECA = OFF_SCR;               // [NV]
+  static constexpr int OFF_VECB = OFF_VECA + NV;         // [NV]
+  static constexpr int OFF_VT = OFF_VECB + NV;           // [NW]
+  static constexpr int OFF_VG = OFF_VT + NW;             // [NW]
+  static constexpr int OFF_VW = OFF_VG + NW;             // [NW]
+  static constexpr int OFF_FINV = OFF_VW + NW;           // [H][36]
+  static constexpr int SCR_SIZE = 2 * NV + 3 * NW + 36 * H;
+  static constexpr int OFF_DINV = OFF_SCR + SCR_SIZE;    // [NW] 1/L_ii
+  static constexpr int OFF_KD = OFF_DINV + NW;           // [NW] diag of polish K
+  static constexpr int OFF_GAM = OFF_KD + NW;            // [H][H]
+  static constexpr int OFF_NN = OFF_GAM + H * H;         // [H][H]
+  static constexpr int OFF_WB = OFF_NN + H * H;          // [6][12] balanced wrench map
+  static constexpr int OFF_DSM = OFF_WB + 72;            // [NV] D (scaling) for broadcast reads
+  static constexpr int SMEM_DOUBLES = OFF_DSM + NV;
+  static_assert(12 * NW + NW / 2 + 8 <= SCR_SIZE, "polish scratch does not fit");
+};
+
+// ----------------------------------------------------------------- lane-local helpers
+MPC_LANEFN double limit_scaling(double v) {  // scaling.c:7-14
+  v = v < kMinScaling ? 1.0 : v;
+  return v > kMaxScaling ? kMaxScaling : v;
+}
+
+// inverse of a symmetric 3x3 given as (xx,xy,xz,yy,yz,zz)
+MPC_LANEFN void inv3sym(const double a[6], double o[6]) {
+  const double c00 = a[3] * a[5] - a[4] * a[4];
+  const double c01 = a[2] * a[4] - a[1] * a[5];
+  const double c02 = a[1] * a[4] - a[2] * a[3];
+  const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  const double id = 1.0 / det;
+  o[0] = c00 * id;
+  o[1] = c01 * id;
+  o[2] = c02 * id;
+  o[3] = (a[0] * a[5] - a[2] * a[2]) * id;
+  o[4] = (a[1] * a[2] - a[0] * a[4]) * id;
+  o[5] = (a[0] * a[3] - a[1] * a[1]) * id;
+}
+MPC_LANEFN void mul3sym(const double m[6], const double v[3], double o[3]) {
+  o[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  o[1] = m[1] * v[0] + m[3] * v[1] + m[4] * v[2];
+  o[2] = m[2] * v[0] + m[4] * v[1] + m[5] * v[2];
+}
+
+// inverse of a 6x6 SPD matrix (full row-major in, full row-major out) via Cholesky
+MPC_LANEFN void inv6spd(const double* a, double* out) {
+  double L[6][6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = a[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    const double d = sqrt(s);
+    const double id = 1.0 / d;
+    L[j][j] = id;  // store the reciprocal on the diagonal
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = a[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = t * id;
+    }
+  }
+  double Wi[6][6];  // W = L^-1 (lower)
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    Wi[c][c] = L[c][c];
+#pragma unroll
+    for (int i = c + 1; i < 6; ++i) {
+      double t = 0;
+#pragma unroll
+      for (int k = c; k < i; ++k) t += L[i][k] * Wi[k][c];
+      Wi[i][c] = -t * L[i][i];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) {
+      double t = 0;
+#pragma unroll
+      for (int k = r; k < 6; ++k) t += Wi[k][r] * Wi[k][c];
+      out[r * 6 + c] = t;
+      out[c * 6 + r] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// The solver.  `rec` = problem record (float, MPC_REC_* layout), `rp` = robot constant row.
+// `sm` = this warp's shared-memory block (Dims<H>::SMEM_DOUBLES doubles); Gamma/N tables at
+// OFF_GAM/OFF_NN must have been filled by fill_tables<H>() before the first call.
+// Outputs: grf0[12] (negated horizon-0 forces), grf_full[12H] or null, status, info or null.
+// ---------------------------------------------------------------------------------------
+template <int H>
+MPC_FN void fill_tables(double* sm, double dt
+#if defined(__CUDACC__) && !defined(MPC_EMULATE)
+                        , const int lane
+#endif
+) {
+  using D = Dims<H>;
+  LANES_BEGIN
+  for (int e = lane; e < H * H; e += 32) {
+    const int i = e / H, j = e % H;
+    const int k0 = i > j ? i : j;
+    double g = 0;
+    for (int k = k0; k < H; ++k)
+      g += (dt * dt * ((k - i) + 0.5)) * (dt * dt * ((k - j) + 0.5));
+    sm[D::OFF_GAM + e] = g;
+    sm[D::OFF_NN + e] = (double)(H - k0);
+  }
+  LANES_END
+  WSYNC();
+}
+
+template <int H>
+MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& prm, double* sm,
+                        float* grf0, float* grf_full, int32_t* status_out, float* resid_out,
+                        double* info_out, double* dbg_out
+#if defined(__CUDACC__) && !defined(MPC_EMULATE)
+                        , const int lane
+#endif
+) {
+  using D = Dims<H>;
+  constexpr int NS = D::NSLOT, NW = D::NW, NWP = D::NWP, NWS = D::NWS, NV = D::NV, NVS = D::NVS;
+  double* const Wm = sm + D::OFF_WM;
+  double* const vecA = sm + D::OFF_VECA;
+  double* const vecB = sm + D::OFF_VECB;
+  double* const vt = sm + D::OFF_VT;
+  double* const vg = sm + D::OFF_VG;
+  double* const vw = sm + D::OFF_VW;
+  double* const Finv = sm + D::OFF_FINV;
+  double* const dinv = sm + D::OFF_DINV;
+  double* const kd = sm + D::OFF_KD;
+  const double* const gam = sm + D::OFF_GAM;
+  const double* const nnm = sm + D::OFF_NN;
+  double* const Wb = sm + D::OFF_WB;
+  double* const Dsm = sm + D::OFF_DSM;
+
+  const double dt = prm.dt, alpha = prm.alpha;
+
+  // ------------------------------------------------------------------ uniform inputs
+  const double mass = rp[0];
+  const double mu0 = rec[MPC_REC_MU + 0], mu1 = rec[MPC_REC_MU + 1];
+  const double mu2 = rec[MPC_REC_MU + 2], mu3 = rec[MPC_REC_MU + 3];
+  const double fz_max = mass * kGravity * kMaxScale;            // mpc_osqp.cc:685-686
+  const double fz_min = mass * kGravity * kMinScale;
+  const double f_ub = (mu0 + 1.0) * fz_max;                     // mpc_osqp.cc:466-467
+  const double roll = rec[MPC_REC_RPY], pitch = rec[MPC_REC_RPY + 1], yaw = rec[MPC_REC_RPY + 2];
+  const double sr = sin(roll), cr = cos(roll), sp = sin(pitch), cp = cos(pitch);
+  const double sy = sin(yaw), cy = cos(yaw);
+  const double tp = tan(pitch);
+  // T: angular velocity -> rpy rate (mpc_osqp.cc:306-312)
+  const double T00 = cy / cp, T01 = sy / cp, T10 = -sy, T11 = cy, T20 = cy * tp, T21 = sy * tp;
+  const double w_rpy0 = rec[MPC_REC_WEIGHTS + 0], w_rpy1 = rec[MPC_REC_WEIGHTS + 1],
+               w_rpy2 = rec[MPC_REC_WEIGHTS + 2];
+  double balance;  // torque-row balancing factor s (conditioning only)
+
+  // ------------------------------------------------------------------ per-lane state
+  PER_LANE_ARR(double, wbl, [6][3]);   // balanced wrench map block of this lane's leg
+  PER_LANE_ARR(double, xv, [NS][3]);
+  PER_LANE_ARR(double, zv, [NS][5]);
+  PER_LANE_ARR(double, yv, [NS][5]);
+  PER_LANE_ARR(double, qb, [NS][3]);   // scaled linear cost
+  PER_LANE_ARR(double, Dv, [NS][3]);   // Ruiz D
+  PER_LANE_ARR(double, Ev, [NS][5]);   // Ruiz E
+  PER_LANE_ARR(double, di, [NS][6]);   // Delta^-1 (sym 3x3)
+  PER_LANE_ARR(double, rhoj, [NS]);    // rho of this leg-step's rows
+  PER_LANE_ARR(double, cj, [NS]);      // contact flag as 0/1 double
+  PER_LANE_ARR(int, valid, [NS]);
+  PER_LANE_ARR(double, tmp3, [NS][3]);
+  PER_LANE_ARR(double, xt, [NS][3]);
+  PER_LANE(double, red);               // reduction operand
+  PER_LANE(double, red2);
+
+  // ------------------------------------------------------------------ S1: structure
+  LANES_BEGIN
+  const int leg = lane & 3;
+  // R = Rz Ry Rx (mpc_osqp.cc:283-291); Rf = Rx Ry Rz (mpc_osqp.cc:606-617, Q3)
+  const double R[3][3] = {{cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr},
+                          {sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr},
+                          {-sp, cp * sr, cp * cr}};
+  const double Rf[3][3] = {{cp * cy, -cp * sy, sp},
+                           {sr * sp * cy + cr * sy, -sr * sp * sy + cr * cy, -sr * cp},
+                           {-cr * sp * cy + sr * sy, cr * sp * sy + sr * cy, cr * cp}};
+  // inertia_(inertia.data()): column-major read of the row-major list (mpc_osqp.cc:516)
+  double In[3][3], Ii[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) In[i][j] = rp[1 + j * 3 + i];
+  {
+    const double c00 = In[1][1] * In[2][2] - In[1][2] * In[2][1];
+    const double c01 = In[1][2] * In[2][0] - In[1][0] * In[2][2];
+    const double c02 = In[1][0] * In[2][1] - In[1][1] * In[2][0];
+    const double idet = 1.0 / (In[0][0] * c00 + In[0][1] * c01 + In[0][2] * c02);
+    Ii[0][0] = c00 * idet;
+    Ii[0][1] = (In[0][2] * In[2][1] - In[0][1] * In[2][2]) * idet;
+    Ii[0][2] = (In[0][1] * In[1][2] - In[0][2] * In[1][1]) * idet;
+    Ii[1][0] = c01 * idet;
+    Ii[1][1] = (In[0][0] * In[2][2] - In[0][2] * In[2][0]) * idet;
+    Ii[1][2] = (In[0][2] * In[1][0] - In[0][0] * In[1][2]) * idet;
+    Ii[2][0] = c02 * idet;
+    Ii[2][1] = (In[0][1] * In[2][0] - In[0][0] * In[2][1]) * idet;
+    Ii[2][2] = (In[0][0] * In[1][1] - In[0][1] * In[1][0]) * idet;
+  }
+  double RI[3][3], Iw[3][3];  // Iw = R Ii R^T (mpc_osqp.cc:670-671)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      RI[i][j] = R[i][0] * Ii[0][j] + R[i][1] * Ii[1][j] + R[i][2] * Ii[2][j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      Iw[i][j] = RI[i][0] * R[j][0] + RI[i][1] * R[j][1] + RI[i][2] * R[j][2];
+  const double px = rec[MPC_REC_FOOTPOS + 3 * leg], py = rec[MPC_REC_FOOTPOS + 3 * leg + 1],
+               pz = rec[MPC_REC_FOOTPOS + 3 * leg + 2];
+  const double rx = Rf[0][0] * px + Rf[0][1] * py + Rf[0][2] * pz;
+  const double ry = Rf[1][0] * px + Rf[1][1] * py + Rf[1][2] * pz;
+  const double rz = Rf[2][0] * px + Rf[2][1] * py + Rf[2][2] * pz;
+  // Bw = Iw * skew(r) (mpc_osqp.cc:293-297, 324-336)
+  const double sk[3][3] = {{0, -rz, ry}, {rz, 0, -rx}, {-ry, rx, 0}};
+  double fro = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double v = Iw[a][0] * sk[0][b] + Iw[a][1] * sk[1][b] + Iw[a][2] * sk[2][b];
+      _(wbl)[a][b] = v;
+      _(wbl)[3 + a][b] = (a == b) ? 1.0 / mass : 0.0;
+      fro += v * v;
+    }
+  _(red) = lane < 4 ? fro : 0.0;
+  LANES_END
+  {
+    const double fro_all = WSUM(red);
+    balance = sqrt((12.0 / (mass * mass)) / fro_all);
+  }
+  const double ib = 1.0 / balance, ib2 = ib * ib;
+  // Q1' = S^-1 blkdiag(T^T W_rpy T, W_pos) S^-1 ; Q2' = S^-1 dt^2 blkdiag(W_w, W_v) S^-1
+  double Q1t[6];  // (xx,xy,xz,yy,yz,zz) of T^T W T / s^2
+  {
+    const double a0 = w_rpy0, a1 = w_rpy1, a2 = w_rpy2;
+    // T columns: col0 = (T00,T10,T20), col1 = (T01,T11,T21), col2 = (0,0,1)
+    Q1t[0] = (T00 * a0 * T00 + T10 * a1 * T10 + T20 * a2 * T20) * ib2;
+    Q1t[1] = (T00 * a0 * T01 + T10 * a1 * T11 + T20 * a2 * T21) * ib2;
+    Q1t[2] = (T20 * a2) * ib2;
+    Q1t[3] = (T01 * a0 * T01 + T11 * a1 * T11 + T21 * a2 * T21) * ib2;
+    Q1t[4] = (T21 * a2) * ib2;
+    Q1t[5] = a2 * ib2;
+  }
+  const double q1p[3] = {(double)rec[MPC_REC_WEIGHTS + 3], (double)rec[MPC_REC_WEIGHTS + 4],
+                         (double)rec[MPC_REC_WEIGHTS + 5]};
+  const double q2d[6] = {rec[MPC_REC_WEIGHTS + 6] * dt * dt * ib2, rec[MPC_REC_WEIGHTS + 7] * dt * dt * ib2,
+                         rec[MPC_REC_WEIGHTS + 8] * dt * dt * ib2, rec[MPC_REC_WEIGHTS + 9] * dt * dt,
+                         rec[MPC_REC_WEIGHTS + 10] * dt * dt,      rec[MPC_REC_WEIGHTS + 11] * dt * dt};
+  // Q1'[c][c'] accessor
+  auto Q1at = [&](int c, int c2) -> double {
+    if (c < 3 && c2 < 3) {
+      const int lo = c < c2 ? c : c2, hi = c < c2 ? c2 : c;
+      return Q1t[lo == 0 ? hi : (lo == 1 ? 2 + hi : 5)];
+    }
+    return (c == c2) ? q1p[c - 3] : 0.0;
+  };
+
+  LANES_BEGIN
+  const int leg = lane & 3;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) _(wbl)[a][b] *= balance;
+  if (lane < 4) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Wb[c * 12 + 3 * leg + b] = _(wbl)[c][b];
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int j = lane + 32 * s;
+    _(valid)[s] = j < D::NLS;
+    _(cj)[s] = _(valid)[s] ? (double)rec[MPC_REC_CONTACT + j] : 0.0;
+  }
+  // per-step tracking-error terms a_k (-> vg) and b_k (-> vw), unbalanced wrench coords
+  if (lane < H) {
+    const int k = lane;
+    const double t = dt * (k + 1);
+    const double g = -kGravity;
+    double e[12];
+    const double om[3] = {(double)rec[MPC_REC_ANGVEL], (double)rec[MPC_REC_ANGVEL + 1],
+                          (double)rec[MPC_REC_ANGVEL + 2]};
+    const double ve[3] = {(double)rec[MPC_REC_COM_VEL], (double)rec[MPC_REC_COM_VEL + 1],
+                          (double)rec[MPC_REC_COM_VEL + 2]};
+    const double po[3] = {(double)rec[MPC_REC_COM_POS], (double)rec[MPC_REC_COM_POS + 1],
+                          (double)rec[MPC_REC_COM_POS + 2]};
+    const double nr[3] = {(double)rec[MPC_REC_NORMAL], (double)rec[MPC_REC_NORMAL + 1],
+                          (double)rec[MPC_REC_NORMAL + 2]};
+    const double dv[3] = {(double)rec[MPC_REC_DES_VEL], (double)rec[MPC_REC_DES_VEL + 1],
+                          (double)rec[MPC_REC_DES_VEL + 2]};
+    const double dw[3] = {(double)rec[MPC_REC_DES_ANGVEL], (double)rec[MPC_REC_DES_ANGVEL + 1],
+                          (double)rec[MPC_REC_DES_ANGVEL + 2]};
+    // desired states (mpc_osqp.cc:635-659)
+    const double des[12] = {(double)rec[MPC_REC_DES_RPY], (double)rec[MPC_REC_DES_RPY + 1], yaw + t * dw[2],
+                            t * dv[0] + po[0], t * dv[1] + po[1], (double)rec[MPC_REC_DES_POS + 2],
+                            dw[0], dw[1], dw[2], dv[0], dv[1], 0.0};
+    if (k < H - 1) {  // a_qp block k = A_exp^(k+1); the LAST block stays zero (mpc_osqp.cc:361)
+      e[0] = roll + t * (T00 * om[0] + T01 * om[1]) - des[0];
+      e[1] = pitch + t * (T10 * om[0] + T11 * om[1]) - des[1];
+      e[2] = yaw + t * (T20 * om[0] + T21 * om[1] + om[2]) - des[2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        e[3 + a] = po[a] + t * ve[a] + 0.5 * t * t * nr[a] * g - des[3 + a];
+        e[6 + a] = om[a] - des[6 + a];
+        e[9 + a] = ve[a] + t * nr[a] * g - des[9 + a];
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 12; ++a) e[a] = -des[a];
+    }
+    const double we0 = w_rpy0 * e[0], we1 = w_rpy1 * e[1], we2 = w_rpy2 * e[2];
+    vg[6 * k + 0] = T00 * we0 + T10 * we1 + T20 * we2;
+    vg[6 * k + 1] = T01 * we0 + T11 * we1 + T21 * we2;
+    vg[6 * k + 2] = we2;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      vg[6 * k + 3 + a] = rec[MPC_REC_WEIGHTS + 3 + a] * e[3 + a];
+      vw[6 * k + a] = dt * rec[MPC_REC_WEIGHTS + 6 + a] * e[6 + a];
+      vw[6 * k + 3 + a] = dt * rec[MPC_REC_WEIGHTS + 9 + a] * e[9 + a];
+    }
+  }
+  LANES_END
+  WSYNC();
+  // acc_j = sum_{k>=j} c_{k-j} a_k + b_k ; balanced (rows 0..2 divided by s) -> vt
+  LANES_BEGIN
+  for (int i = lane; i < NW; i += 32) {
+    const int j = i / 6, c = i % 6;
+    double acc = 0;
+    for (int k = j; k < H; ++k) acc += (dt * dt * ((k - j) + 0.5)) * vg[6 * k + c] + vw[6 * k + c];
+    vt[i] = c < 3 ? acc * ib : acc;
+  }
+  LANES_END
+  WSYNC();
+  // q = 2 Wb'^T acc' (mpc_osqp.cc:681-683); initialise D = E = 1
+  LANES_BEGIN
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int j = lane + 32 * s;
+    const int k = (j >> 2) < H ? (j >> 2) : 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double q = 0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) q += _(wbl)[c][a] * vt[6 * k + c];
+      _(qb)[s][a] = _(valid)[s] ? 2.0 * q : 0.0;
+      _(Dv)[s][a] = 1.0;
+      _(xv)[s][a] = 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      _(Ev)[s][r] = 1.0;
+      _(zv)[s][r] = 0.0;
+      _(yv)[s][r] = 0.0;
+    }
+  }
+  for (int v = lane; v < NV; v += 32) Dsm[v] = 1.0;
+  LANES_END
+  WSYNC();
+  if (dbg_out) {  // unscaled q for builder tests
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s])
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dbg_out[3 * (lane + 32 * s) + a] = _(qb)[s][a];
+    LANES_END
+  }
+
+  // ------------------------------------------------------------------ S2: Ruiz scaling
+  // G1 = Wb'^T Q1' Wb', G2 = Wb'^T Q2' Wb' (12x12) staged in the (still unused) Wm block.
+  double* const G1 = Wm;
+  double* const G2 = Wm + 144;
+  LANES_BEGIN
+  for (int e = lane; e < 144; e += 32) {
+    const int a = e / 12, b = e % 12;
+    double g1 = 0, g2 = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double y1 = 0;
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2) y1 += Q1at(c, c2) * Wb[c2 * 12 + b];
+      g1 += Wb[c * 12 + a] * y1;
+      g2 += Wb[c * 12 + a] * q2d[c] * Wb[c * 12 + b];
+    }
+    G1[e] = g1;
+    G2[e] = g2;
+  }
+  LANES_END
+  WSYNC();
+  if (dbg_out) {  // dense P (unscaled) for builder tests: dbg_out[NV + i*NV + v]
+    LANES_BEGIN
+    for (int v = lane; v < NV; v += 32) {
+      const int k2 = v / 12, b = v % 12;
+      for (int k = 0; k < H; ++k)
+        for (int a = 0; a < 12; ++a) {
+          double p = 2.0 * (gam[k * H + k2] * G1[a * 12 + b] + nnm[k * H + k2] * G2[a * 12 + b]);
+          if (12 * k + a == v) p += alpha;
+          dbg_out[NV + (12 * k + a) * NV + v] = p;
+        }
+    }
+    LANES_END
+  }
+
+  double cscale = 1.0;  // OSQP's cost scaling c
+  // column inf-norms of (D P D) WITHOUT the c factor -> vecA   (scaling.c:30-43, lin_alg.c:358)
+  auto col_norms_P = [&]() {
+    LANES_BEGIN
+    for (int v = lane; v < NV; v += 32) {
+      const int k2 = v / 12, b = v % 12;
+      double m = 0;
+      for (int k = 0; k < H; ++k) {
+        const double gk = gam[k * H + k2], nk = nnm[k * H + k2];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+          double p = 2.0 * (gk * G1[a * 12 + b] + nk * G2[a * 12 + b]);
+          if (12 * k + a == v) p += alpha;
+          m = fmax(m, Dsm[12 * k + a] * fabs(p));
+        }
+      }
+      vecA[v] = m * Dsm[v];
+    }
+    LANES_END
+    WSYNC();
+  };
+  if (prm.scaling_iters > 0) col_norms_P();
+  for (int it = 0; it < prm.scaling_iters; ++it) {
+    // D_temp, E_temp from the current scaled P, A (scaling.c:78-93)
+    LANES_BEGIN
+    double qmax = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int j = lane + 32 * s;
+      if (_(valid)[s]) {
+        const double* E = _(Ev)[s];
+        const double* Dd = _(Dv)[s];
+        const double am0 = fabs(mu0), am1 = fabs(mu1), am2 = fabs(mu2), am3 = fabs(mu3);
+        double colA[3];
+        colA[0] = fmax(E[0], E[1]) * Dd[0];
+        colA[1] = fmax(E[2], E[3]) * Dd[1];
+        colA[2] = fmax(fmax(fmax(E[0] * am0, E[1] * am1), fmax(E[2] * am2, E[3] * am3)), E[4]) * Dd[2];
+        double rowA[5];
+        rowA[0] = E[0] * fmax(Dd[0], am0 * Dd[2]);
+        rowA[1] = E[1] * fmax(Dd[0], am1 * Dd[2]);
+        rowA[2] = E[2] * fmax(Dd[1], am2 * Dd[2]);
+        rowA[3] = E[3] * fmax(Dd[1], am3 * Dd[2]);
+        rowA[4] = E[4] * Dd[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double nrm = fmax(cscale * vecA[3 * j + a], colA[a]);
+          const double dtmp = 1.0 / sqrt(limit_scaling(nrm));
+          _(Dv)[s][a] *= dtmp;
+          _(qb)[s][a] *= dtmp;
+          Dsm[3 * j + a] = _(Dv)[s][a];
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r) _(Ev)[s][r] *= 1.0 / sqrt(limit_scaling(rowA[r]));
+      }
+    }
+    LANES_END
+    WSYNC();
+    // cost normalisation (scaling.c:117-146)
+    col_norms_P();
+    LANES_BEGIN
+    double ssum = 0, qmax = 0;
+    for (int v = lane; v < NV; v += 32) ssum += cscale * vecA[v];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s])
+#pragma unroll
+        for (int a = 0; a < 3; ++a) qmax = fmax(qmax, fabs(_(qb)[s][a]));
+    _(red) = ssum;
+    _(red2) = qmax;
+    LANES_END
+    {
+      const double mean = WSUM(red) / (double)NV;
+      const double nq = limit_scaling(WMAX(red2));
+      const double ctemp = 1.0 / limit_scaling(fmax(mean, nq));
+      cscale *= ctemp;
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(qb)[s][a] *= ctemp;
+      LANES_END
+    }
+  }
+  const double cinv = 1.0 / cscale;
+  if (dbg_out) {
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + 32 * s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dbg_out[NV + NV * NV + 3 * j + a] = _(Dv)[s][a];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) dbg_out[NV + NV * NV + NV + 5 * j + r] = _(Ev)[s][r];
+      }
+    if (lane == 0) dbg_out[NV + NV * NV + NV + 20 * H] = cscale;
+    LANES_END
+  }
+
+  // ------------------------------------------------------------------ helpers
+  // scaled bounds of row r of a slot (mpc_osqp.cc:449-477 scaled by E, osqp.c:scale_data)
+  auto lo_of = [&](const double* E, double c, int r) -> double { return r == 4 ? E[4] * (fz_min * c) : 0.0; };
+  auto hi_of = [&](const double* E, double c, int r) -> double {
+    return r == 4 ? E[4] * (fz_max * c) : E[r] * (f_ub * c);
+  };
+  // Abar v : rows of a leg-step (A block mpc_osqp.cc:437-447 scaled E A D)
+  auto A_mul = [&](const double* E, const double* Dd, const double* v, double* o) {
+    const double dx = Dd[0] * v[0], dy = Dd[1] * v[1], dz = Dd[2] * v[2];
+    o[0] = E[0] * (-dx + mu0 * dz);
+    o[1] = E[1] * (dx + mu1 * dz);
+    o[2] = E[2] * (-dy + mu2 * dz);
+    o[3] = E[3] * (dy + mu3 * dz);
+    o[4] = E[4] * dz;
+  };
+  auto At_mul = [&](const double* E, const double* Dd, const double* w, double* o) {
+    const double w0 = E[0] * w[0], w1 = E[1] * w[1], w2 = E[2] * w[2], w3 = E[3] * w[3], w4 = E[4] * w[4];
+    o[0] = Dd[0] * (w1 - w0);
+    o[1] = Dd[1] * (w3 - w2);
+    o[2] = Dd[2] * (mu0 * w0 + mu1 * w1 + mu2 * w2 + mu3 * w3 + w4);
+  };
+
+  // dense Cholesky (left-looking) of the leading n x n block of Wm (lower, column-major with
+  // stride NWP), then dinv[i] = 1/L_ii.  L overwrites the lower triangle.
+  auto cholesky = [&](int n) {
+    for (int j = 0; j < n; ++j) {
+      LANES_BEGIN
+      for (int i = j + lane; i < n; i += 32) {
+        double acc = Wm[j * NWP + i];
+        for (int k = 0; k < j; ++k) acc -= Wm[k * NWP + i] * Wm[k * NWP + j];
+        Wm[j * NWP + i] = acc;
+      }
+      LANES_END
+      WSYNC();
+      LANES_BEGIN
+      const double ajj = Wm[j * NWP + j];
+      const double inv = 1.0 / sqrt(ajj);
+      for (int i = j + 1 + lane; i < n; i += 32) Wm[j * NWP + i] *= inv;
+      if (lane == 0) dinv[j] = inv;
+      LANES_END
+      WSYNC();
+      LANES_BEGIN
+      if (lane == 0) Wm[j * NWP + j] = 1.0 / dinv[j];
+      LANES_END
+    }
+    WSYNC();
+  };
+
+  // factor(): Delta^-1 per leg-step, F_k^-1, Hm, Cholesky, W = L^-1 into the upper triangle.
+  // wrow = per-row weights are rho_j on every row of a leg-step (ADMM factorisation).
+  auto factor = [&](double sig) {
+    double* const Fs = Wm;  // [NLS][21] staging (Wm is rebuilt below)
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int j = lane + 32 * s;
+      if (_(valid)[s]) {
+        const double* E = _(Ev)[s];
+        const double* Dd = _(Dv)[s];
+        const double w = _(rhoj)[s];
+        const double e0 = w * E[0] * E[0], e1 = w * E[1] * E[1], e2 = w * E[2] * E[2],
+                     e3 = w * E[3] * E[3], e4 = w * E[4] * E[4];
+        double dl[6];
+        const double base = cscale * alpha;
+        dl[0] = base * Dd[0] * Dd[0] + sig + (e0 + e1) * Dd[0] * Dd[0];
+        dl[1] = 0.0;
+        dl[2] = (-e0 * mu0 + e1 * mu1) * Dd[0] * Dd[2];
+        dl[3] = base * Dd[1] * Dd[1] + sig + (e2 + e3) * Dd[1] * Dd[1];
+        dl[4] = (-e2 * mu2 + e3 * mu3) * Dd[1] * Dd[2];
+        dl[5] = base * Dd[2] * Dd[2] + sig +
+                (e0 * mu0 * mu0 + e1 * mu1 * mu1 + e2 * mu2 * mu2 + e3 * mu3 * mu3 + e4) * Dd[2] * Dd[2];
+        inv3sym(dl, _(di)[s]);
+        // X = wbl * diag(D) (6x3), Y = X Delta^-1, F contribution = Y X^T (sym 6x6 -> 21)
+        double X[6][3], Y[6][3];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) X[c][a] = _(wbl)[c][a] * Dd[a];
+          mul3sym(_(di)[s], X[c], Y[c]);
+        }
+        int e = 0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+          for (int c2 = 0; c2 <= c; ++c2) {
+            Fs[j * 21 + e] = Y[c][0] * X[c2][0] + Y[c][1] * X[c2][1] + Y[c][2] * X[c2][2];
+            ++e;
+          }
+      }
+    }
+    LANES_END
+    WSYNC();
+    // F_k = sum over the 4 legs; invert (lane k < H)
+    LANES_BEGIN
+    if (lane < H) {
+      const int k = lane;
+      double F[36], Fi[36];
+      int e = 0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int c2 = 0; c2 <= c; ++c2) {
+          const double v = Fs[(4 * k + 0) * 21 + e] + Fs[(4 * k + 1) * 21 + e] + Fs[(4 * k + 2) * 21 + e] +
+                           Fs[(4 * k + 3) * 21 + e];
+          F[c * 6 + c2] = v;
+          F[c2 * 6 + c] = v;
+          ++e;
+        }
+      inv6spd(F, Fi);
+#pragma unroll
+      for (int q = 0; q < 36; ++q) Finv[k * 36 + q] = Fi[q];
+    }
+    LANES_END
+    WSYNC();
+    // Hm = blkdiag(Finv) + 2c (Gamma (x) Q1' + N (x) Q2')  (lower triangle)
+    LANES_BEGIN
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      for (int i2 = 0; i2 <= i; ++i2) {
+        const int k2 = i2 / 6, c2 = i2 % 6;
+        double v = 2.0 * cscale * (gam[k * H + k2] * Q1at(c, c2) + (c == c2 ? nnm[k * H + k2] * q2d[c] : 0.0));
+        if (k == k2) v += Finv[k * 36 + c * 6 + c2];
+        Wm[i2 * NWP + i] = v;
+      }
+    }
+    LANES_END
+    WSYNC();
+    cholesky(NW);
+    // W = L^-1, stored transposed in the strict upper triangle: W[i][c] at Wm[i*NWP + c], c < i
+    for (int i = 1; i < NW; ++i) {
+      LANES_BEGIN
+      double acc[NWS];
+#pragma unroll
+      for (int r = 0; r < NWS; ++r) {
+        const int c = lane + 32 * r;
+        acc[r] = (c < i) ? Wm[c * NWP + i] * dinv[c] : 0.0;
+      }
+      for (int k = 1; k < i; ++k) {
+        const double lik = Wm[k * NWP + i];
+#pragma unroll
+        for (int r = 0; r < NWS; ++r) {
+          const int c = lane + 32 * r;
+          if (c < k) acc[r] += lik * Wm[k * NWP + c];
+        }
+      }
+      const double dii = dinv[i];
+#pragma unroll
+      for (int r = 0; r < NWS; ++r) {
+        const int c = lane + 32 * r;
+        if (c < i) Wm[i * NWP + c] = -acc[r] * dii;
+      }
+      LANES_END
+      // no sync needed: every lane only re-reads what it wrote itself (its own columns c)
+    }
+    WSYNC();
+  };
+
+  // ksolve(): xt = K^-1 tmp3  (K = Delta + U^T Q U) through the wrench-space system
+  auto ksolve = [&]() {
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (_(valid)[s]) {
+        const int j = lane + 32 * s;
+        double sv[3];
+        mul3sym(_(di)[s], _(tmp3)[s], sv);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          _(xt)[s][a] = sv[a];
+          vecA[3 * j + a] = _(Dv)[s][a] * sv[a];
+        }
+      }
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN  // t = U s
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      double t = 0;
+#pragma unroll
+      for (int b = 0; b < 12; ++b) t += Wb[c * 12 + b] * vecA[12 * k + b];
+      vt[i] = t;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN  // g = F^-1 t
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      double g = 0;
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2) g += Finv[k * 36 + c * 6 + c2] * vt[6 * k + c2];
+      vg[i] = g;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN  // y = W g   (lane i walks its own storage column i*NWP + c, c < i)
+    for (int i = lane; i < NW; i += 32) {
+      double acc = dinv[i] * vg[i];
+      const double* col = Wm + i * NWP;
+      for (int c = 0; c < i; ++c) acc += col[c] * vg[c];
+      vw[i] = acc;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN  // w = W^T y (lane c reads Wm[i*NWP + c], i > c: contiguous across lanes)
+    for (int c = lane; c < NW; c += 32) {
+      double acc = dinv[c] * vw[c];
+      for (int i = c + 1; i < NW; ++i) acc += Wm[i * NWP + c] * vw[i];
+      vt[c] = acc;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN  // v = g - F^-1 w  -> vecB (NW <= NV)
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      double v = vg[i];
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2) v -= Finv[k * 36 + c * 6 + c2] * vt[6 * k + c2];
+      vecB[i] = v;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN  // x = s - Delta^-1 U^T v
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (_(valid)[s]) {
+        const int j = lane + 32 * s;
+        const int k = j >> 2;
+        double u[3], du[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double t = 0;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) t += _(wbl)[c][a] * vecB[6 * k + c];
+          u[a] = _(Dv)[s][a] * t;
+        }
+        mul3sym(_(di)[s], u, du);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(xt)[s][a] -= du[a];
+      }
+    }
+    LANES_END
+    WSYNC();
+  };
+
+  // apply_P(): xt = Pbar * tmp3   (structured mat-vec, used by residuals and polish)
+  auto apply_P = [&]() {
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + 32 * s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) vecA[3 * j + a] = _(Dv)[s][a] * _(tmp3)[s][a];
+      }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      double t = 0;
+#pragma unroll
+      for (int b = 0; b < 12; ++b) t += Wb[c * 12 + b] * vecA[12 * k + b];
+      vt[i] = t;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      double a1 = 0;
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2) a1 += Q1at(c, c2) * vt[6 * k + c2];
+      vg[i] = a1;
+      vw[i] = q2d[c] * vt[i];
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN
+    for (int i = lane; i < NW; i += 32) {
+      const int k = i / 6, c = i % 6;
+      double o = 0;
+      for (int k2 = 0; k2 < H; ++k2) o += gam[k * H + k2] * vg[6 * k2 + c] + nnm[k * H + k2] * vw[6 * k2 + c];
+      vecB[i] = 2.0 * cscale * o;
+    }
+    LANES_END
+    WSYNC();
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + 32 * s;
+        const int k = j >> 2;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double t = 0;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) t += _(wbl)[c][a] * vecB[6 * k + c];
+          const double d = _(Dv)[s][a];
+          _(xt)[s][a] = cscale * alpha * d * d * _(tmp3)[s][a] + d * t;
+        }
+      }
+    LANES_END
+    WSYNC();
+  };
+
+  // ------------------------------------------------------------------ S3: rho, factor
+  double rho = fmin(fmax(prm.rho0, kRhoMin), kRhoMax);  // auxil.c:82
+  LANES_BEGIN
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    // equality rows <=> swing leg (u - l < RHO_TOL on the SCALED bounds, auxil.c:90-93);
+    // all five rows of a leg-step share the type unless E makes a stance row tiny
+    const double* E = _(Ev)[s];
+    const bool eq = (hi_of(E, _(cj)[s], 4) - lo_of(E, _(cj)[s], 4) < kRhoTol);
+    _(rhoj)[s] = eq ? kRhoEqFactor * rho : rho;
+    _(tmp3)[s][0] = eq ? 1.0 : 0.0;  // remember the type in tmp (re-derived below)
+  }
+  LANES_END
+  factor(prm.sigma);
+
+  // ------------------------------------------------------------------ S4: ADMM
+  const double ar = prm.relax, sigma = prm.sigma;
+  int iter = 0, status = MPC_STATUS_MAX_ITER, rho_updates = 0;
+  double pri_res = 0, dua_res = 0;
+  PER_LANE_ARR(double, Axv, [NS][5]);
+  PER_LANE_ARR(double, Atyv, [NS][3]);
+  PER_LANE_ARR(double, Pxv, [NS][3]);
+  PER_LANE_ARR(double, nrm, [14]);
+  const int max_iter = prm.fixed_iters > 0 ? prm.fixed_iters : prm.max_iter;
+  for (iter = 1; iter <= max_iter; ++iter) {
+    LANES_BEGIN  // rhs = sigma x - q + A^T (rho z - y)      (auxil.c:149-162)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (_(valid)[s]) {
+        double w[5], at[3];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) w[r] = _(rhoj)[s] * _(zv)[s][r] - _(yv)[s][r];
+        At_mul(_(Ev)[s], _(Dv)[s], w, at);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(tmp3)[s][a] = sigma * _(xv)[s][a] - _(qb)[s][a] + at[a];
+      }
+    }
+    LANES_END
+    ksolve();
+    LANES_BEGIN  // update_x, update_z, update_y (auxil.c:188-228)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (_(valid)[s]) {
+        double zt[5];
+        A_mul(_(Ev)[s], _(Dv)[s], _(xt)[s], zt);
+        const double rinv = 1.0 / _(rhoj)[s];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(xv)[s][a] = ar * _(xt)[s][a] + (1.0 - ar) * _(xv)[s][a];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const double zr = ar * zt[r] + (1.0 - ar) * _(zv)[s][r];
+          const double lo = lo_of(_(Ev)[s], _(cj)[s], r), hi = hi_of(_(Ev)[s], _(cj)[s], r);
+          const double zn = fmin(fmax(zr + rinv * _(yv)[s][r], lo), hi);
+          _(yv)[s][r] += _(rhoj)[s] * (zr - zn);
+          _(zv)[s][r] = zn;
+        }
+      }
+    }
+    LANES_END
+    const bool check = prm.fixed_iters > 0 ? (iter == max_iter) : (iter % prm.check_every == 0);
+    if (!check) continue;
+    // ---- residuals (auxil.c:243-362), unscaled norms for termination, scaled for rho
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) _(tmp3)[s][a] = _(xv)[s][a];
+    LANES_END
+    apply_P();
+    LANES_BEGIN
+#pragma unroll
+    for (int q = 0; q < 14; ++q) _(nrm)[q] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (_(valid)[s]) {
+        A_mul(_(Ev)[s], _(Dv)[s], _(xv)[s], _(Axv)[s]);
+        At_mul(_(Ev)[s], _(Dv)[s], _(yv)[s], _(Atyv)[s]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(Pxv)[s][a] = _(xt)[s][a];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const double ei = 1.0 / _(Ev)[s][r];
+          const double rp_ = _(Axv)[s][r] - _(zv)[s][r];
+          _(nrm)[0] = fmax(_(nrm)[0], fabs(ei * rp_));
+          _(nrm)[2] = fmax(_(nrm)[2], fabs(ei * _(zv)[s][r]));
+          _(nrm)[3] = fmax(_(nrm)[3], fabs(ei * _(Axv)[s][r]));
+          _(nrm)[7] = fmax(_(nrm)[7], fabs(rp_));
+          _(nrm)[8] = fmax(_(nrm)[8], fabs(_(zv)[s][r]));
+          _(nrm)[9] = fmax(_(nrm)[9], fabs(_(Axv)[s][r]));
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double dii = 1.0 / _(Dv)[s][a];
+          const double rd = _(qb)[s][a] + _(Pxv)[s][a] + _(Atyv)[s][a];
+          _(nrm)[1] = fmax(_(nrm)[1], fabs(dii * rd));
+          _(nrm)[4] = fmax(_(nrm)[4], fabs(dii * _(qb)[s][a]));
+          _(nrm)[5] = fmax(_(nrm)[5], fabs(dii * _(Atyv)[s][a]));
+          _(nrm)[6] = fmax(_(nrm)[6], fabs(dii * _(Pxv)[s][a]));
+          _(nrm)[10] = fmax(_(nrm)[10], fabs(rd));
+          _(nrm)[11] = fmax(_(nrm)[11], fabs(_(qb)[s][a]));
+          _(nrm)[12] = fmax(_(nrm)[12], fabs(_(Atyv)[s][a]));
+          _(nrm)[13] = fmax(_(nrm)[13], fabs(_(Pxv)[s][a]));
+        }
+      }
+    }
+    LANES_END
+    double nr_[14];
+    for (int q = 0; q < 14; ++q) {
+      LANES_BEGIN
+      _(red) = _(nrm)[q];
+      LANES_END
+      nr_[q] = WMAX(red);
+    }
+    pri_res = nr_[0];
+    dua_res = cinv * nr_[1];
+    if (prm.fixed_iters <= 0) {
+      const double eps_prim = prm.eps_abs + prm.eps_rel * fmax(nr_[2], nr_[3]);
+      const double eps_dual = prm.eps_abs + prm.eps_rel * cinv * fmax(fmax(nr_[4], nr_[5]), nr_[6]);
+      if (pri_res < eps_prim && dua_res < eps_dual) {  // auxil.c:735-747
+        status = MPC_STATUS_SOLVED;
+        break;
+      }
+    } else {
+      status = MPC_STATUS_SOLVED;
+      break;
+    }
+    if (prm.adaptive_rho && iter < max_iter) {  // compute_rho_estimate / adapt_rho (auxil.c:13-77)
+      const double pr = nr_[7] / (fmax(nr_[8], nr_[9]) + 1e-10);
+      const double dr = nr_[10] / (fmax(fmax(nr_[11], nr_[12]), nr_[13]) + 1e-10);
+      double rho_new = rho * sqrt(pr / (dr + 1e-10));
+      rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+      if (rho_new > rho * prm.rho_tol_ratio || rho_new < rho / prm.rho_tol_ratio) {
+        rho = rho_new;
+        ++rho_updates;
+        LANES_BEGIN
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const double* E = _(Ev)[s];
+          const bool eq = (hi_of(E, _(cj)[s], 4) - lo_of(E, _(cj)[s], 4) < kRhoTol);
+          _(rhoj)[s] = eq ? kRhoEqFactor * rho : rho;
+        }
+        LANES_END
+        factor(prm.sigma);
+      }
+    }
+  }
+  if (iter > max_iter) iter = max_iter;
+
+  // ------------------------------------------------------------------ S5: polish
+  int polish_status = 0, nfree_total = 0;
+  if (prm.polish && status == MPC_STATUS_SOLVED) {
+    // polish.c:20-95 active-set guess; per leg-step null-space basis of the active rows
+    PER_LANE_ARR(double, Yb, [NS][3][3]);   // orthonormal basis: first rk = row space, rest = null space
+    PER_LANE_ARR(double, pp, [NS][3]);      // particular (pinned) part of x
+    PER_LANE_ARR(int, rk, [NS]);
+    PER_LANE_ARR(int, act, [NS]);           // bit r: row active; bit 8+r: upper (else lower)
+    PER_LANE_ARR(int, foff, [NS]);
+    PER_LANE(int, cnt);
+    PER_LANE(int, off);
+    LANES_BEGIN
+    _(cnt) = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      _(rk)[s] = 0;
+      _(act)[s] = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        _(pp)[s][a] = 0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) _(Yb)[s][a][b] = (a == b) ? 1.0 : 0.0;
+      }
+      if (_(valid)[s]) {
+        const double* E = _(Ev)[s];
+        const double* Dd = _(Dv)[s];
+        double rows[5][3], bt[5];
+        int na = 0;
+        const double arow[5][3] = {{-E[0] * Dd[0], 0.0, E[0] * mu0 * Dd[2]},
+                                   {E[1] * Dd[0], 0.0, E[1] * mu1 * Dd[2]},
+                                   {0.0, -E[2] * Dd[1], E[2] * mu2 * Dd[2]},
+                                   {0.0, E[3] * Dd[1], E[3] * mu3 * Dd[2]},
+                                   {0.0, 0.0, E[4] * Dd[2]}};
+        double rmax = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const double lo = lo_of(E, _(cj)[s], r), hi = hi_of(E, _(cj)[s], r);
+          const bool low = (_(zv)[s][r] - lo < -_(yv)[s][r]);
+          const bool upp = (hi - _(zv)[s][r] < _(yv)[s][r]);
+          if (low || upp) {
+            _(act)[s] |= (1 << r) | ((low ? 0 : 1) << (8 + r));
+            rows[na][0] = arow[r][0]; rows[na][1] = arow[r][1]; rows[na][2] = arow[r][2];
+            bt[na] = low ? lo : hi;
+            rmax = fmax(rmax, sqrt(arow[r][0] * arow[r][0] + arow[r][1] * arow[r][1] + arow[r][2] * arow[r][2]));
+            ++na;
+          }
+        }
+        // modified Gram-Schmidt over the active rows -> orthonormal row-space basis
+        double Yr[3][3];
+        int rank = 0;
+        for (int q = 0; q < na && rank < 3; ++q) {
+          double v[3] = {rows[q][0], rows[q][1], rows[q][2]};
+          for (int p = 0; p < rank; ++p) {
+            const double d = v[0] * Yr[p][0] + v[1] * Yr[p][1] + v[2] * Yr[p][2];
+            v[0] -= d * Yr[p][0]; v[1] -= d * Yr[p][1]; v[2] -= d * Yr[p][2];
+          }
+          const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+          if (nv > 1e-9 * rmax) {
+            Yr[rank][0] = v[0] / nv; Yr[rank][1] = v[1] / nv; Yr[rank][2] = v[2] / nv;
+            ++rank;
+          }
+        }
+        // complete to an orthonormal basis of R^3 (null space of the active rows)
+        if (rank == 0) {
+          // identity already
+        } else if (rank == 1) {
+          const double* y = Yr[0];
+          int ax = 0;
+          if (fabs(y[1]) < fabs(y[ax])) ax = 1;
+          if (fabs(y[2]) < fabs(y[ax])) ax = 2;
+          double e[3] = {0, 0, 0};
+          e[ax] = 1.0;
+          double n1[3] = {y[1] * e[2] - y[2] * e[1], y[2] * e[0] - y[0] * e[2], y[0] * e[1] - y[1] * e[0]};
+          const double l1 = sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+          n1[0] /= l1; n1[1] /= l1; n1[2] /= l1;
+          const double n2[3] = {y[1] * n1[2] - y[2] * n1[1], y[2] * n1[0] - y[0] * n1[2], y[0] * n1[1] - y[1] * n1[0]};
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { _(Yb)[s][0][a] = y[a]; _(Yb)[s][1][a] = n1[a]; _(Yb)[s][2][a] = n2[a]; }
+        } else if (rank == 2) {
+          const double* y1 = Yr[0];
+          const double* y2 = Yr[1];
+          const double n1[3] = {y1[1] * y2[2] - y1[2] * y2[1], y1[2] * y2[0] - y1[0] * y2[2], y1[0] * y2[1] - y1[1] * y2[0]};
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { _(Yb)[s][0][a] = y1[a]; _(Yb)[s][1][a] = y2[a]; _(Yb)[s][2][a] = n1[a]; }
+        } else {
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) _(Yb)[s][p][a] = Yr[p][a];
+        }
+        _(rk)[s] = rank;
+        // particular solution: least squares of rows*(Y eta) = bt in the row-space basis
+        if (rank > 0) {
+          double BtB[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Btb[3] = {0, 0, 0};
+          for (int q = 0; q < na; ++q) {
+            double bq[3];
+            for (int p = 0; p < rank; ++p)
+              bq[p] = rows[q][0] * _(Yb)[s][p][0] + rows[q][1] * _(Yb)[s][p][1] + rows[q][2] * _(Yb)[s][p][2];
+            for (int p = 0; p < rank; ++p) {
+              Btb[p] += bq[p] * bt[q];
+              for (int p2 = 0; p2 < rank; ++p2) BtB[p][p2] += bq[p] * bq[p2];
+            }
+          }
+          for (int p = rank; p < 3; ++p) BtB[p][p] = 1.0;
+          const double sym[6] = {BtB[0][0], BtB[0][1], BtB[0][2], BtB[1][1], BtB[1][2], BtB[2][2]};
+          double isym[6], eta[3];
+          inv3sym(sym, isym);
+          mul3sym(isym, Btb, eta);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            double v = 0;
+            for (int p = 0; p < rank; ++p) v += _(Yb)[s][p][a] * eta[p];
+            _(pp)[s][a] = v;
+          }
+        }
+        _(cnt) += 3 - rank;
+      }
+    }
+    LANES_END
+    WEXSCAN_I(off, cnt);
+    nfree_total = WSUM_I(cnt);
+    if (nfree_total <= NW) {
+      const int nf = nfree_total;
+      double* const Mf = sm + D::OFF_SCR;            // [nf][6]  m_f = U nu_f
+      double* const A1f = Mf + 6 * NW;               // [nf][6]  Q1' m_f
+      int* const kf = reinterpret_cast<int*>(A1f + 6 * NW);  // [nf] step index
+      // gP = Pbar p + qbar  (needs apply_P before the scratch is overwritten)
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(tmp3)[s][a] = _(pp)[s][a];
+      LANES_END
+      apply_P();
+      PER_LANE_ARR(double, bxi, [NS][3]);   // -N^T (q + P p) per free coordinate of the slot
+      PER_LANE_ARR(double, xi, [NS][3]);
+      LANES_BEGIN
+      int o = _(off);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        _(foff)[s] = o;
+        if (_(valid)[s]) {
+          const int j = lane + 32 * s;
+          const int k = j >> 2;
+          for (int p = _(rk)[s]; p < 3; ++p) {
+            const double* nu = _(Yb)[s][p];
+            double gdot = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) gdot += nu[a] * (_(qb)[s][a] + _(xt)[s][a]);
+            _(bxi)[s][p] = -gdot;
+            _(xi)[s][p] = 0;
+          }
+          o += 3 - _(rk)[s];
+          (void)k;
+        }
+      }
+      LANES_END
+      WSYNC();
+      LANES_BEGIN  // m_f, Q1' m_f into scratch (scratch == vecA.. region, apply_P is done)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (_(valid)[s]) {
+          const int j = lane + 32 * s;
+          const int k = j >> 2;
+          int f = _(foff)[s];
+          for (int p = _(rk)[s]; p < 3; ++p, ++f) {
+            const double* nu = _(Yb)[s][p];
+            double m[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              m[c] = 0;
+#pragma unroll
+              for (int a = 0; a < 3; ++a) m[c] += _(wbl)[c][a] * _(Dv)[s][a] * nu[a];
+              Mf[6 * f + c] = m[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              double a1 = 0;
+#pragma unroll
+              for (int c2 = 0; c2 < 6; ++c2) a1 += Q1at(c, c2) * m[c2];
+              A1f[6 * f + c] = a1;
+            }
+            kf[f] = k;
+          }
+        }
+      }
+      LANES_END
+      WSYNC();
+      // K_f (wrench part): lower (to be factorised, + delta) and mirrored upper (for K xi)
+      LANES_BEGIN
+      for (int f = lane; f < nf; f += 32) {
+        double m[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) m[c] = Mf[6 * f + c];
+        const int k = kf[f];
+        for (int f2 = 0; f2 <= f; ++f2) {
+          const int k2 = kf[f2];
+          double d1 = 0, d2 = 0;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            d1 += m[c] * A1f[6 * f2 + c];
+            d2 += m[c] * q2d[c] * Mf[6 * f2 + c];
+          }
+          const double v = 2.0 * cscale * (gam[k * H + k2] * d1 + nnm[k * H + k2] * d2);
+          if (f2 == f) {
+            kd[f] = v;
+          } else {
+            Wm[f2 * NWP + f] = v;  // lower: row f, col f2
+            Wm[f * NWP + f2] = v;  // upper mirror
+          }
+        }
+      }
+      LANES_END
+      WSYNC();
+      // same-leg-step term nu^T diag(c alpha D^2) nu' added by the owner lane
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (_(valid)[s]) {
+          const int f0 = _(foff)[s];
+          for (int p = _(rk)[s]; p < 3; ++p)
+            for (int p2 = _(rk)[s]; p2 <= p; ++p2) {
+              double v = 0;
+#pragma unroll
+              for (int a = 0; a < 3; ++a)
+                v += _(Yb)[s][p][a] * cscale * alpha * _(Dv)[s][a] * _(Dv)[s][a] * _(Yb)[s][p2][a];
+              const int f = f0 + (p - _(rk)[s]), f2 = f0 + (p2 - _(rk)[s]);
+              if (f == f2) {
+                kd[f] += v;
+              } else {
+                Wm[f2 * NWP + f] += v;
+                Wm[f * NWP + f2] += v;
+              }
+            }
+        }
+      }
+      LANES_END
+      WSYNC();
+      LANES_BEGIN
+      for (int f = lane; f < nf; f += 32) Wm[f * NWP + f] = kd[f] + prm.delta;
+      LANES_END
+      WSYNC();
+      cholesky(nf);
+      // the polish vectors live in Dsm (NV = 2 NW doubles; D itself is also held in registers)
+      double* const pv = Dsm;        // [nf] right-hand side / solution
+      double* const pxi = Dsm + NW;  // [nf] current xi
+      auto tri_solve = [&]() {  // pv <- (L L^T)^-1 pv
+        for (int j = 0; j < nf; ++j) {
+          LANES_BEGIN
+          const double yj = pv[j] * dinv[j];
+          for (int i = j + 1 + lane; i < nf; i += 32) pv[i] -= Wm[j * NWP + i] * yj;
+          LANES_END
+          WSYNC();
+          LANES_BEGIN
+          if (lane == 0) pv[j] = pv[j] * dinv[j];
+          LANES_END
+          WSYNC();
+        }
+        for (int j = nf - 1; j >= 0; --j) {
+          LANES_BEGIN
+          const double xj = pv[j] * dinv[j];
+          for (int i = lane; i < j; i += 32) pv[i] -= Wm[i * NWP + j] * xj;
+          LANES_END
+          WSYNC();
+          LANES_BEGIN
+          if (lane == 0) pv[j] = pv[j] * dinv[j];
+          LANES_END
+          WSYNC();
+        }
+      };
+      // first solve: (K_f + delta) xi = b
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (_(valid)[s])
+          for (int p = _(rk)[s]; p < 3; ++p) {
+            const int f = _(foff)[s] + (p - _(rk)[s]);
+            pv[f] = _(bxi)[s][p];
+          }
+      LANES_END
+      WSYNC();
+      tri_solve();
+      LANES_BEGIN
+      for (int f = lane; f < nf; f += 32) pxi[f] = pv[f];
+      LANES_END
+      WSYNC();
+      for (int itr = 0; itr < prm.polish_refine; ++itr) {  // polish.c:127-175
+        LANES_BEGIN
+        // r = b - K_f xi (true K, no delta)
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (_(valid)[s])
+            for (int p = _(rk)[s]; p < 3; ++p) {
+              const int f = _(foff)[s] + (p - _(rk)[s]);
+              double acc = kd[f] * pxi[f];
+              for (int f2 = 0; f2 < f; ++f2) acc += Wm[f * NWP + f2] * pxi[f2];
+              for (int f2 = f + 1; f2 < nf; ++f2) acc += Wm[f2 * NWP + f] * pxi[f2];
+              _(xi)[s][p] = _(bxi)[s][p] - acc;
+            }
+        LANES_END
+        WSYNC();
+        LANES_BEGIN
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (_(valid)[s])
+            for (int p = _(rk)[s]; p < 3; ++p) pv[_(foff)[s] + (p - _(rk)[s])] = _(xi)[s][p];
+        LANES_END
+        WSYNC();
+        tri_solve();
+        LANES_BEGIN
+        for (int f = lane; f < nf; f += 32) pxi[f] += pv[f];
+        LANES_END
+        WSYNC();
+      }
+      // x_pol = p + N xi ; g = Pbar x_pol + qbar ; multipliers ; acceptance (polish.c:300-330)
+      PER_LANE_ARR(double, xp, [NS][3]);
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(xp)[s][a] = _(pp)[s][a];
+        if (_(valid)[s])
+          for (int p = _(rk)[s]; p < 3; ++p) {
+            const double x_ = pxi[_(foff)[s] + (p - _(rk)[s])];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) _(xp)[s][a] += _(Yb)[s][p][a] * x_;
+          }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(tmp3)[s][a] = _(xp)[s][a];
+      }
+      LANES_END
+      WSYNC();
+      // restore D in shared memory (Dsm was used as polish vector space) before apply_P
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (_(valid)[s])
+#pragma unroll
+          for (int a = 0; a < 3; ++a) Dsm[3 * (lane + 32 * s) + a] = _(Dv)[s][a];
+      LANES_END
+      WSYNC();
+      apply_P();
+      PER_LANE_ARR(double, ypv, [NS][5]);
+      LANES_BEGIN
+      double npri = 0, ndua = 0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (_(valid)[s]) {
+          const double* E = _(Ev)[s];
+          const double* Dd = _(Dv)[s];
+          const double arow[5][3] = {{-E[0] * Dd[0], 0.0, E[0] * mu0 * Dd[2]},
+                                     {E[1] * Dd[0], 0.0, E[1] * mu1 * Dd[2]},
+                                     {0.0, -E[2] * Dd[1], E[2] * mu2 * Dd[2]},
+                                     {0.0, E[3] * Dd[1], E[3] * mu3 * Dd[2]},
+                                     {0.0, 0.0, E[4] * Dd[2]}};
+          double g[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) g[a] = _(qb)[s][a] + _(xt)[s][a];
+          // y_act = B (B^T B)^-1 (-Y^T g), B = A_act Y (rank columns)
+          const int rank = _(rk)[s];
+          double yred[5] = {0, 0, 0, 0, 0};
+          if (rank > 0) {
+            double BtB[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, rhs3[3] = {0, 0, 0};
+            double Bq[5][3];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+              for (int p = 0; p < 3; ++p) Bq[r][p] = 0;
+              if (_(act)[s] & (1 << r)) {
+                for (int p = 0; p < rank; ++p) {
+                  Bq[r][p] = arow[r][0] * _(Yb)[s][p][0] + arow[r][1] * _(Yb)[s][p][1] + arow[r][2] * _(Yb)[s][p][2];
+                }
+                for (int p = 0; p < rank; ++p)
+                  for (int p2 = 0; p2 < rank; ++p2) BtB[p][p2] += Bq[r][p] * Bq[r][p2];
+              }
+            }
+            for (int p = 0; p < rank; ++p)
+              rhs3[p] = -(_(Yb)[s][p][0] * g[0] + _(Yb)[s][p][1] * g[1] + _(Yb)[s][p][2] * g[2]);
+            for (int p = rank; p < 3; ++p) BtB[p][p] = 1.0;
+            const double sym[6] = {BtB[0][0], BtB[0][1], BtB[0][2], BtB[1][1], BtB[1][2], BtB[2][2]};
+            double isym[6], tt[3];
+            inv3sym(sym, isym);
+            mul3sym(isym, rhs3, tt);
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+              if (_(act)[s] & (1 << r)) yred[r] = Bq[r][0] * tt[0] + Bq[r][1] * tt[1] + Bq[r][2] * tt[2];
+          }
+          double zp[5];
+          A_mul(E, Dd, _(xp)[s], zp);
+          double yp[5];
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {  // project_normalcone (proj.c:17-31)
+            const double lo = lo_of(E, _(cj)[s], r), hi = hi_of(E, _(cj)[s], r);
+            const double t = zp[r] + yred[r];
+            const double zc = fmin(fmax(t, lo), hi);
+            yp[r] = t - zc;
+            _(ypv)[s][r] = yp[r];
+            npri = fmax(npri, fabs((zp[r] - zc) / E[r]));
+            zp[r] = zc;
+          }
+          double aty[3];
+          At_mul(E, Dd, yp, aty);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) ndua = fmax(ndua, fabs((g[a] + aty[a]) / Dd[a]));
+#pragma unroll
+          for (int r = 0; r < 5; ++r) _(Axv)[s][r] = zp[r];  // polished z kept for warm start
+        }
+      }
+      _(red) = npri;
+      _(red2) = ndua;
+      LANES_END
+      const double pri_p = WMAX(red), dua_p = cinv * WMAX(red2);
+      const bool ok = (pri_p < pri_res && dua_p < dua_res) || (pri_p < pri_res && dua_res < 1e-10) ||
+                      (dua_p < dua_res && pri_res < 1e-10);
+      if (ok) {
+        polish_status = 1;
+        pri_res = pri_p;
+        dua_res = dua_p;
+        LANES_BEGIN
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) _(xv)[s][a] = _(xp)[s][a];
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            _(zv)[s][r] = _(Axv)[s][r];
+            _(yv)[s][r] = _(ypv)[s][r];
+          }
+        }
+        LANES_END
+      } else {
+        polish_status = -1;
+      }
+    } else {
+      polish_status = -1;  // free set larger than the on-chip buffer (never for reference gaits)
+    }
+  }
+
+  // ------------------------------------------------------------------ S6: output
+  // unscale (scaling.c:183-199) and negate (mpc_osqp.cc:789-790)
+  LANES_BEGIN
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (_(valid)[s]) {
+      const int j = lane + 32 * s;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float f = (float)(-_(Dv)[s][a] * _(xv)[s][a]);
+        if (j < 4) grf0[3 * j + a] = f;
+        if (grf_full) grf_full[3 * j + a] = f;
+      }
+    }
+  }
+  if (lane == 0) {
+    if (status_out) *status_out = status;
+    if (resid_out) {
+      resid_out[0] = (float)pri_res;
+      resid_out[1] = (float)dua_res;
+    }
+    if (info_out) {
+      info_out[INFO_ITERS] = iter;
+      info_out[INFO_RHO_UPDATES] = rho_updates;
+      info_out[INFO_RHO] = rho;
+      info_out[INFO_POLISH] = polish_status;
+      info_out[INFO_PRI] = pri_res;
+      info_out[INFO_DUA] = dua_res;
+      info_out[INFO_C] = cscale;
+      info_out[INFO_NFREE] = nfree_total;
+    }
+  }
+  LANES_END
+  WSYNC();
+}
+
+}  // namespace mpc
