@@ -105,3 +105,33 @@ def debug_build_qp(record: np.ndarray, horizon: int, robot_params_row: np.ndarra
     rc = _lib.lib().mpc_b200_debug_build_qp(C.byref(s), vp(rec), vp(rp), vp(P), vp(q), vp(D), vp(E), vp(c))
     _lib.check(rc, "mpc_b200_debug_build_qp")
     return dict(P=P, q=q, D=D, E=E, c=float(c[0]))
+
+
+def solve_host_pinned(records, robot_type, robot_params, horizon, steps, warmup=2, **settings):
+    """End-to-end timing helper (bench.py `e2e`): the C-ABI host entry point fed from PINNED
+    host buffers; every step copies the records H2D, solves, and copies forces + status D2H.
+    Returns (seconds for `steps` steps, h2d bytes per step, d2h bytes per step)."""
+    import time
+    s = _lib.default_settings(horizon=horizon, **settings)
+    n = records.shape[0]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    t_rec, t_rt, t_rp = pin(records.astype(np.float32)), pin(robot_type.astype(np.int32)), pin(
+        np.asarray(robot_params, dtype=np.float32))
+    t_grf = torch.empty((n, 12), dtype=torch.float32).pin_memory()
+    t_st = torch.empty((n,), dtype=torch.int32).pin_memory()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+
+    def one():
+        rc = _lib.lib().mpc_b200_solve_batch_host(C.byref(s), vp(t_rec), vp(t_rp), vp(t_rt), n, vp(t_grf), None,
+                                                  vp(t_st))
+        _lib.check(rc, "mpc_b200_solve_batch_host")
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    h2d = t_rec.numel() * 4 + t_rt.numel() * 4 + t_rp.numel() * 4
+    d2h = t_grf.numel() * 4 + t_st.numel() * 4
+    return dt, h2d, d2h

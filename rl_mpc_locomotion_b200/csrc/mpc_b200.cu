@@ -264,7 +264,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records
                          double* d_info, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
-  if (!d_records || !d_robot_params || !d_grf0 || n_robots < 0) {
+  if (n_robots < 0 || (n_robots > 0 && (!d_records || !d_robot_params || !d_grf0))) {
     snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
     return MPC_B200_EINVAL;
   }
@@ -272,6 +272,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records
     snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
     return MPC_B200_ENOGPU;
   }
+  if (n_robots == 0) return MPC_B200_OK;
   return dispatch(settings, d_records, d_robot_params, d_robot_type, n_robots, d_grf0, d_grf_full, d_status,
                   d_resid, d_info, nullptr, (cudaStream_t)stream);
 }

@@ -65,12 +65,14 @@ struct Dims {
   static constexpr int NLS = 4 * H;             // (step, leg) pairs
   static constexpr int NSLOT = (NLS + 31) / 32; // leg-steps per lane
   static constexpr int NW = 6 * H;              // wrench-space dimension
-  static constexpr int NWP = NW + 1;            // padded column stride (bank-conflict free)
   static constexpr int NWS = (NW + 31) / 32;
   static constexpr int NVS = (NV + 31) / 32;
+  static constexpr int NP = (NW + 1) / 2;             // row pairs (i, NW-1-i) of the triangle
+  static constexpr int NRS = 2 * ((NP + 31) / 32);    // triangle rows owned per lane
+  static constexpr int NTRI = NW * (NW - 1) / 2;      // packed strictly-lower triangle
   // shared-memory layout (doubles)
-  static constexpr int OFF_WM = 0;                       // [NW][NWP] Hm -> L (lower) / W^T (upper)
-  static constexpr int OFF_SCR = OFF_WM + NW * NWP;      // scratch: vecA vecB vt vg vw Finv
+  static constexpr int OFF_WP = 0;                       // [NTRI] Hm -> L -> W = L^-1, row-packed
+  static constexpr int OFF_SCR = OFF_WP + NTRI;          // scratch: vecA vecB vt vg vw Finv
   static constexpr int OFF_VECA = OFF_SCR;               // [NV]
   static constexpr int OFF_VECB = OFF_VECA + NV;         // [NV]
   static constexpr int OFF_VT = OFF_VECB + NV;           // [NW]
@@ -78,15 +80,34 @@ struct Dims {
   static constexpr int OFF_VW = OFF_VG + NW;             // [NW]
   static constexpr int OFF_FINV = OFF_VW + NW;           // [H][36]
   static constexpr int SCR_SIZE = 2 * NV + 3 * NW + 36 * H;
-  static constexpr int OFF_DINV = OFF_SCR + SCR_SIZE;    // [NW] 1/L_ii
-  static constexpr int OFF_KD = OFF_DINV + NW;           // [NW] diag of polish K
-  static constexpr int OFF_GAM = OFF_KD + NW;            // [H][H]
+  static constexpr int OFF_DINV = OFF_SCR + SCR_SIZE;    // [NW] diag: H_ii -> 1/L_ii = W_ii
+  static constexpr int OFF_COL = OFF_DINV + NW;          // [2][NW] column staging (inversion, polish)
+  static constexpr int OFF_GAM = OFF_COL + 2 * NW;       // [H][H]
   static constexpr int OFF_NN = OFF_GAM + H * H;         // [H][H]
   static constexpr int OFF_WB = OFF_NN + H * H;          // [6][12] balanced wrench map
-  static constexpr int OFF_DSM = OFF_WB + 72;            // [NV] D (scaling) for broadcast reads
+  static constexpr int OFF_Q1S = OFF_WB + 72;            // [6][6] Q1'
+  static constexpr int OFF_DSM = OFF_Q1S + 36;           // [NV] D (scaling) for broadcast reads
   static constexpr int SMEM_DOUBLES = OFF_DSM + NV;
   static_assert(12 * NW + NW / 2 + 8 <= SCR_SIZE, "polish scratch does not fit");
+  static_assert(NLS * 21 <= NTRI && 288 + 72 <= NTRI, "staging does not fit in the triangle buffer");
 };
+
+// Row-packed strictly-lower triangle: element (i, k), k < i, lives at i(i-1)/2 + k.  Triangular
+// numbers are a complete residue system mod 2^m, so 16 consecutive rows at the same column hit
+// 16 different 8-byte banks (row walks are conflict-free) and a fixed row is contiguous in k
+// (column walks across lanes are conflict-free too).
+MPC_LANEFN int tri(int i) { return (i * (i - 1)) >> 1; }
+// Rows of an n x n triangle owned by `lane`: rows are paired (p, n-1-p) so that every lane
+// carries the same number of elements (n-1) per pair.
+MPC_LANEFN int rowmap(int lane, int n, int r) {
+  const int p = lane + 32 * (r >> 1);
+  if (p >= ((n + 1) >> 1)) return -1;
+  if (r & 1) {
+    const int q = n - 1 - p;
+    return q > p ? q : -1;
+  }
+  return p;
+}
 
 // ----------------------------------------------------------------- lane-local helpers
 MPC_LANEFN double limit_scaling(double v) {  // scaling.c:7-14
@@ -193,8 +214,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #endif
 ) {
   using D = Dims<H>;
-  constexpr int NS = D::NSLOT, NW = D::NW, NWP = D::NWP, NWS = D::NWS, NV = D::NV, NVS = D::NVS;
-  double* const Wm = sm + D::OFF_WM;
+  constexpr int NS = D::NSLOT, NW = D::NW, NV = D::NV, NRS = D::NRS;
+  double* const Wp = sm + D::OFF_WP;
   double* const vecA = sm + D::OFF_VECA;
   double* const vecB = sm + D::OFF_VECB;
   double* const vt = sm + D::OFF_VT;
@@ -202,7 +223,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   double* const vw = sm + D::OFF_VW;
   double* const Finv = sm + D::OFF_FINV;
   double* const dinv = sm + D::OFF_DINV;
-  double* const kd = sm + D::OFF_KD;
+  double* const colb = sm + D::OFF_COL;
+  double* const q1s = sm + D::OFF_Q1S;
   const double* const gam = sm + D::OFF_GAM;
   const double* const nnm = sm + D::OFF_NN;
   double* const Wb = sm + D::OFF_WB;
@@ -449,19 +471,32 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   }
 
   // ------------------------------------------------------------------ S2: Ruiz scaling
-  // G1 = Wb'^T Q1' Wb', G2 = Wb'^T Q2' Wb' (12x12) staged in the (still unused) Wm block.
-  double* const G1 = Wm;
-  double* const G2 = Wm + 144;
+  // G1 = Wb'^T Q1' Wb', G2 = Wb'^T Q2' Wb' (12x12) staged in the (still unused) triangle buffer.
+  double* const G1 = Wp;
+  double* const G2 = Wp + 144;
+  double* const Y1 = Wp + 288;  // Q1' Wb' (6x12)
+  LANES_BEGIN
+  for (int e = lane; e < 36; e += 32) q1s[e] = Q1at(e / 6, e % 6);
+  for (int e = lane; e < 72; e += 32) {
+    const int c = e / 12, b = e % 12;
+    double y1 = 0;
+    if (c < 3) {
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2) y1 += Q1at(c, c2) * Wb[c2 * 12 + b];
+    } else {
+      y1 = q1p[c - 3] * Wb[c * 12 + b];
+    }
+    Y1[e] = y1;
+  }
+  LANES_END
+  WSYNC();
   LANES_BEGIN
   for (int e = lane; e < 144; e += 32) {
     const int a = e / 12, b = e % 12;
     double g1 = 0, g2 = 0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      double y1 = 0;
-#pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2) y1 += Q1at(c, c2) * Wb[c2 * 12 + b];
-      g1 += Wb[c * 12 + a] * y1;
+      g1 += Wb[c * 12 + a] * Y1[c * 12 + b];
       g2 += Wb[c * 12 + a] * q2d[c] * Wb[c * 12 + b];
     }
     G1[e] = g1;
@@ -489,17 +524,25 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_BEGIN
     for (int v = lane; v < NV; v += 32) {
       const int k2 = v / 12, b = v % 12;
-      double m = 0;
+      double g1[12], g2[12];
+#pragma unroll
+      for (int a = 0; a < 12; ++a) {
+        g1[a] = 2.0 * G1[a * 12 + b];
+        g2[a] = 2.0 * G2[a * 12 + b];
+      }
+      double m0 = 0, m1 = 0;
       for (int k = 0; k < H; ++k) {
         const double gk = gam[k * H + k2], nk = nnm[k * H + k2];
+        const double* dk = Dsm + 12 * k;
 #pragma unroll
-        for (int a = 0; a < 12; ++a) {
-          double p = 2.0 * (gk * G1[a * 12 + b] + nk * G2[a * 12 + b]);
-          if (12 * k + a == v) p += alpha;
-          m = fmax(m, Dsm[12 * k + a] * fabs(p));
+        for (int a = 0; a < 12; a += 2) {
+          m0 = fmax(m0, dk[a] * fabs(gk * g1[a] + nk * g2[a]));
+          m1 = fmax(m1, dk[a + 1] * fabs(gk * g1[a + 1] + nk * g2[a + 1]));
         }
       }
-      vecA[v] = m * Dsm[v];
+      // diagonal entry carries + alpha (P_vv >= 0, so |P_vv + alpha| only grows the max)
+      const double pd = gam[k2 * H + k2] * g1[b] + nnm[k2 * H + k2] * g2[b] + alpha;
+      vecA[v] = fmax(fmax(m0, m1), Dsm[v] * pd) * Dsm[v];
     }
     LANES_END
     WSYNC();
@@ -604,27 +647,62 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     o[2] = Dd[2] * (mu0 * w0 + mu1 * w1 + mu2 * w2 + mu3 * w3 + w4);
   };
 
-  // dense Cholesky (left-looking) of the leading n x n block of Wm (lower, column-major with
-  // stride NWP), then dinv[i] = 1/L_ii.  L overwrites the lower triangle.
+  // dense Cholesky (left-looking) of the leading n x n block held as: strictly-lower triangle in
+  // Wp (row-packed), diagonal in dinv[].  On exit Wp holds L (strictly lower) and dinv[i] = 1/L_ii.
+  // Row i is owned by lane i % 32; inner loops have warp-uniform trip counts (j).
   auto cholesky = [&](int n) {
     for (int j = 0; j < n; ++j) {
+      const double* rowj = Wp + tri(j);
       LANES_BEGIN
-      for (int i = j + lane; i < n; i += 32) {
-        double acc = Wm[j * NWP + i];
-        for (int k = 0; k < j; ++k) acc -= Wm[k * NWP + i] * Wm[k * NWP + j];
-        Wm[j * NWP + i] = acc;
+      // first owned row >= j
+      for (int i = j + ((lane - j) & 31); i < n; i += 32) {
+        double* rowi = Wp + tri(i);
+        double a0 = (i == j) ? dinv[j] : rowi[j], a1 = 0.0;
+        int k = 0;
+#pragma unroll 2
+        for (; k + 1 < j; k += 2) {
+          a0 -= rowi[k] * rowj[k];
+          a1 -= rowi[k + 1] * rowj[k + 1];
+        }
+        if (k < j) a0 -= rowi[k] * rowj[k];
+        a0 += a1;
+        if (i == j) dinv[j] = 1.0 / sqrt(a0);
+        else rowi[j] = a0;                       // unscaled; scaled after the barrier
       }
       LANES_END
       WSYNC();
       LANES_BEGIN
-      const double ajj = Wm[j * NWP + j];
-      const double inv = 1.0 / sqrt(ajj);
-      for (int i = j + 1 + lane; i < n; i += 32) Wm[j * NWP + i] *= inv;
-      if (lane == 0) dinv[j] = inv;
+      const double inv = dinv[j];
+      for (int i = j + 1 + ((lane - j - 1) & 31); i < n; i += 32) Wp[tri(i) + j] *= inv;
+      LANES_END
+      WSYNC();
+    }
+  };
+
+  // in-place inverse of the lower factor: W = L^-1 (strictly-lower part in Wp, W_ii = dinv[i]).
+  // Column sweep j = n-2 .. 0 of  W[i][j] = -(sum_{k=j+1..i} W[i][k] L[k][j]) / L[j][j]; column j of
+  // L is staged in colb (double buffered) because its owners overwrite it with W.
+  auto invert_lower = [&](int n) {
+    for (int j = n - 2; j >= 0; --j) {
+      double* const buf = colb + (j & 1) * NW;
+      LANES_BEGIN
+      for (int i = j + 1 + ((lane - j - 1) & 31); i < n; i += 32) buf[i] = Wp[tri(i) + j];
       LANES_END
       WSYNC();
       LANES_BEGIN
-      if (lane == 0) Wm[j * NWP + j] = 1.0 / dinv[j];
+      const double dj = dinv[j];
+      for (int i = j + 1 + ((lane - j - 1) & 31); i < n; i += 32) {
+        double* rowi = Wp + tri(i);
+        double a0 = dinv[i] * buf[i], a1 = 0.0;
+        int k = j + 1;
+#pragma unroll 2
+        for (; k + 1 < i; k += 2) {
+          a0 += rowi[k] * buf[k];
+          a1 += rowi[k + 1] * buf[k + 1];
+        }
+        if (k < i) a0 += rowi[k] * buf[k];
+        rowi[j] = -(a0 + a1) * dj;
+      }
       LANES_END
     }
     WSYNC();
@@ -633,7 +711,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   // factor(): Delta^-1 per leg-step, F_k^-1, Hm, Cholesky, W = L^-1 into the upper triangle.
   // wrow = per-row weights are rho_j on every row of a leg-step (ADMM factorisation).
   auto factor = [&](double sig) {
-    double* const Fs = Wm;  // [NLS][21] staging (Wm is rebuilt below)
+    double* const Fs = Wp;  // [NLS][21] staging (the triangle is rebuilt below)
     LANES_BEGIN
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -696,47 +774,28 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
-    // Hm = blkdiag(Finv) + 2c (Gamma (x) Q1' + N (x) Q2')  (lower triangle)
+    // Hm = blkdiag(Finv) + 2c (Gamma (x) Q1' + N (x) Q2')  (strictly-lower rows + diagonal)
     LANES_BEGIN
     for (int i = lane; i < NW; i += 32) {
       const int k = i / 6, c = i % 6;
-      for (int i2 = 0; i2 <= i; ++i2) {
-        const int k2 = i2 / 6, c2 = i2 % 6;
-        double v = 2.0 * cscale * (gam[k * H + k2] * Q1at(c, c2) + (c == c2 ? nnm[k * H + k2] * q2d[c] : 0.0));
-        if (k == k2) v += Finv[k * 36 + c * 6 + c2];
-        Wm[i2 * NWP + i] = v;
+      double* const row = Wp + tri(i);
+      const double* q1r = q1s + c * 6;
+      for (int k2 = 0; k2 <= k; ++k2) {
+        const double g2 = 2.0 * cscale * gam[k * H + k2], n2 = 2.0 * cscale * nnm[k * H + k2] * q2d[c];
+        const int cend = (k2 == k) ? c : 5;
+        for (int c2 = 0; c2 <= cend; ++c2) {
+          double v = g2 * q1r[c2] + (c == c2 ? n2 : 0.0);
+          if (k == k2) v += Finv[k * 36 + c * 6 + c2];
+          const int i2 = 6 * k2 + c2;
+          if (i2 < i) row[i2] = v;
+          else dinv[i] = v;
+        }
       }
     }
     LANES_END
     WSYNC();
     cholesky(NW);
-    // W = L^-1, stored transposed in the strict upper triangle: W[i][c] at Wm[i*NWP + c], c < i
-    for (int i = 1; i < NW; ++i) {
-      LANES_BEGIN
-      double acc[NWS];
-#pragma unroll
-      for (int r = 0; r < NWS; ++r) {
-        const int c = lane + 32 * r;
-        acc[r] = (c < i) ? Wm[c * NWP + i] * dinv[c] : 0.0;
-      }
-      for (int k = 1; k < i; ++k) {
-        const double lik = Wm[k * NWP + i];
-#pragma unroll
-        for (int r = 0; r < NWS; ++r) {
-          const int c = lane + 32 * r;
-          if (c < k) acc[r] += lik * Wm[k * NWP + c];
-        }
-      }
-      const double dii = dinv[i];
-#pragma unroll
-      for (int r = 0; r < NWS; ++r) {
-        const int c = lane + 32 * r;
-        if (c < i) Wm[i * NWP + c] = -acc[r] * dii;
-      }
-      LANES_END
-      // no sync needed: every lane only re-reads what it wrote itself (its own columns c)
-    }
-    WSYNC();
+    invert_lower(NW);
   };
 
   // ksolve(): xt = K^-1 tmp3  (K = Delta + U^T Q U) through the wrench-space system
@@ -777,20 +836,34 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
-    LANES_BEGIN  // y = W g   (lane i walks its own storage column i*NWP + c, c < i)
+    LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
     for (int i = lane; i < NW; i += 32) {
-      double acc = dinv[i] * vg[i];
-      const double* col = Wm + i * NWP;
-      for (int c = 0; c < i; ++c) acc += col[c] * vg[c];
-      vw[i] = acc;
+      const double* rowi = Wp + tri(i);
+      double a0 = dinv[i] * vg[i], a1 = 0.0;
+      int k = 0;
+#pragma unroll 2
+      for (; k + 1 < i; k += 2) {
+        a0 += rowi[k] * vg[k];
+        a1 += rowi[k + 1] * vg[k + 1];
+      }
+      if (k < i) a0 += rowi[k] * vg[k];
+      vw[i] = a0 + a1;
     }
     LANES_END
     WSYNC();
-    LANES_BEGIN  // w = W^T y (lane c reads Wm[i*NWP + c], i > c: contiguous across lanes)
+    LANES_BEGIN  // w = W^T y (column walk: W[i][c] contiguous across lanes for a fixed row i)
     for (int c = lane; c < NW; c += 32) {
-      double acc = dinv[c] * vw[c];
-      for (int i = c + 1; i < NW; ++i) acc += Wm[i * NWP + c] * vw[i];
-      vt[c] = acc;
+      double a0 = dinv[c] * vw[c], a1 = 0.0;
+      int i = c + 1;
+      const double* p = Wp + tri(i) + c;     // &W[i][c]; next row is i further on
+#pragma unroll 2
+      for (; i + 1 < NW; i += 2) {
+        a0 += p[0] * vw[i];
+        a1 += p[i] * vw[i + 1];
+        p += 2 * i + 1;
+      }
+      if (i < NW) a0 += p[0] * vw[i];
+      vt[c] = a0 + a1;
     }
     LANES_END
     WSYNC();
@@ -1171,7 +1244,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       LANES_END
       apply_P();
       PER_LANE_ARR(double, bxi, [NS][3]);   // -N^T (q + P p) per free coordinate of the slot
-      PER_LANE_ARR(double, xi, [NS][3]);
       LANES_BEGIN
       int o = _(off);
 #pragma unroll
@@ -1186,7 +1258,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
             for (int a = 0; a < 3; ++a) gdot += nu[a] * (_(qb)[s][a] + _(xt)[s][a]);
             _(bxi)[s][p] = -gdot;
-            _(xi)[s][p] = 0;
           }
           o += 3 - _(rk)[s];
           (void)k;
@@ -1224,13 +1295,14 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
       LANES_END
       WSYNC();
-      // K_f (wrench part): lower (to be factorised, + delta) and mirrored upper (for K xi)
+      // M = K_f + delta*I: wrench part (strictly-lower rows in Wp, diagonal in dinv)
       LANES_BEGIN
       for (int f = lane; f < nf; f += 32) {
         double m[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) m[c] = Mf[6 * f + c];
         const int k = kf[f];
+        double* const row = Wp + tri(f);
         for (int f2 = 0; f2 <= f; ++f2) {
           const int k2 = kf[f2];
           double d1 = 0, d2 = 0;
@@ -1240,12 +1312,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
             d2 += m[c] * q2d[c] * Mf[6 * f2 + c];
           }
           const double v = 2.0 * cscale * (gam[k * H + k2] * d1 + nnm[k * H + k2] * d2);
-          if (f2 == f) {
-            kd[f] = v;
-          } else {
-            Wm[f2 * NWP + f] = v;  // lower: row f, col f2
-            Wm[f * NWP + f2] = v;  // upper mirror
-          }
+          if (f2 == f) dinv[f] = v + prm.delta;
+          else row[f2] = v;
         }
       }
       LANES_END
@@ -1263,30 +1331,23 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
               for (int a = 0; a < 3; ++a)
                 v += _(Yb)[s][p][a] * cscale * alpha * _(Dv)[s][a] * _(Dv)[s][a] * _(Yb)[s][p2][a];
               const int f = f0 + (p - _(rk)[s]), f2 = f0 + (p2 - _(rk)[s]);
-              if (f == f2) {
-                kd[f] += v;
-              } else {
-                Wm[f2 * NWP + f] += v;
-                Wm[f * NWP + f2] += v;
-              }
+              if (f == f2) dinv[f] += v;
+              else Wp[tri(f) + f2] += v;
             }
         }
       }
       LANES_END
       WSYNC();
-      LANES_BEGIN
-      for (int f = lane; f < nf; f += 32) Wm[f * NWP + f] = kd[f] + prm.delta;
-      LANES_END
-      WSYNC();
       cholesky(nf);
-      // the polish vectors live in Dsm (NV = 2 NW doubles; D itself is also held in registers)
-      double* const pv = Dsm;        // [nf] right-hand side / solution
+      // polish vectors: Dsm is free here (D is also held in registers), colb holds xi_0
+      double* const pv = Dsm;        // [nf] right-hand side / solution of the triangular solves
       double* const pxi = Dsm + NW;  // [nf] current xi
+      double* const pxi0 = colb;     // [nf] first regularised solve
       auto tri_solve = [&]() {  // pv <- (L L^T)^-1 pv
         for (int j = 0; j < nf; ++j) {
           LANES_BEGIN
           const double yj = pv[j] * dinv[j];
-          for (int i = j + 1 + lane; i < nf; i += 32) pv[i] -= Wm[j * NWP + i] * yj;
+          for (int i = j + 1 + lane; i < nf; i += 32) pv[i] -= Wp[tri(i) + j] * yj;
           LANES_END
           WSYNC();
           LANES_BEGIN
@@ -1297,7 +1358,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int j = nf - 1; j >= 0; --j) {
           LANES_BEGIN
           const double xj = pv[j] * dinv[j];
-          for (int i = lane; i < j; i += 32) pv[i] -= Wm[i * NWP + j] * xj;
+          const double* rowj = Wp + tri(j);
+          for (int i = lane; i < j; i += 32) pv[i] -= rowj[i] * xj;
           LANES_END
           WSYNC();
           LANES_BEGIN
@@ -1306,47 +1368,32 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
           WSYNC();
         }
       };
-      // first solve: (K_f + delta) xi = b
+      // first solve: (K_f + delta) xi_0 = b
       LANES_BEGIN
 #pragma unroll
       for (int s = 0; s < NS; ++s)
         if (_(valid)[s])
-          for (int p = _(rk)[s]; p < 3; ++p) {
-            const int f = _(foff)[s] + (p - _(rk)[s]);
-            pv[f] = _(bxi)[s][p];
-          }
+          for (int p = _(rk)[s]; p < 3; ++p) pv[_(foff)[s] + (p - _(rk)[s])] = _(bxi)[s][p];
       LANES_END
       WSYNC();
       tri_solve();
       LANES_BEGIN
-      for (int f = lane; f < nf; f += 32) pxi[f] = pv[f];
+      for (int f = lane; f < nf; f += 32) {
+        pxi[f] = pv[f];
+        pxi0[f] = pv[f];
+      }
       LANES_END
       WSYNC();
-      for (int itr = 0; itr < prm.polish_refine; ++itr) {  // polish.c:127-175
+      // iterative refinement (polish.c:127-175): xi <- xi + M^-1 (b - K_f xi) with M = K_f + delta I
+      // which is algebraically xi <- xi_0 + delta * M^-1 xi (no copy of K_f needed)
+      for (int itr = 0; itr < prm.polish_refine; ++itr) {
         LANES_BEGIN
-        // r = b - K_f xi (true K, no delta)
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (_(valid)[s])
-            for (int p = _(rk)[s]; p < 3; ++p) {
-              const int f = _(foff)[s] + (p - _(rk)[s]);
-              double acc = kd[f] * pxi[f];
-              for (int f2 = 0; f2 < f; ++f2) acc += Wm[f * NWP + f2] * pxi[f2];
-              for (int f2 = f + 1; f2 < nf; ++f2) acc += Wm[f2 * NWP + f] * pxi[f2];
-              _(xi)[s][p] = _(bxi)[s][p] - acc;
-            }
-        LANES_END
-        WSYNC();
-        LANES_BEGIN
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (_(valid)[s])
-            for (int p = _(rk)[s]; p < 3; ++p) pv[_(foff)[s] + (p - _(rk)[s])] = _(xi)[s][p];
+        for (int f = lane; f < nf; f += 32) pv[f] = pxi[f];
         LANES_END
         WSYNC();
         tri_solve();
         LANES_BEGIN
-        for (int f = lane; f < nf; f += 32) pxi[f] += pv[f];
+        for (int f = lane; f < nf; f += 32) pxi[f] = pxi0[f] + prm.delta * pv[f];
         LANES_END
         WSYNC();
       }

@@ -66,23 +66,32 @@ def mpc_table(gait_id, iteration, horizon: int = 10) -> np.ndarray:
     return table.reshape(table.shape[:-2] + (4 * horizon,))
 
 
-def contact_state(gait_id, phase) -> np.ndarray:
-    """Gait.getContactState (Gait.py:30-44): stance progress in [0,1], 0 while in swing."""
+def _f32_phase_arrays(gait_id, phase):
     off, dur = gait_arrays(gait_id)
-    offf, durf = off / N_SEGMENT, dur / N_SEGMENT
-    p = np.asarray(phase, dtype=np.float64)[..., None] - offf
-    p = np.where(p < 0, p + 1.0, p)
-    return np.where(p > durf, 0.0, p / durf)
+    # the reference keeps offsets/durations as float32 arrays (ConvexMPCLocomotion.py:30-56) and
+    # mixes them with the Python-float phase, so every operation below happens in float32
+    offf = off.astype(np.float32) / np.float32(N_SEGMENT)
+    durf = dur.astype(np.float32) / np.float32(N_SEGMENT)
+    ph = np.asarray(phase, dtype=np.float64).astype(np.float32)[..., None]
+    return offf, durf, ph
+
+
+def contact_state(gait_id, phase) -> np.ndarray:
+    """Gait.getContactState (Gait.py:30-44): stance progress in [0,1], 0 while in swing.
+    float32 arithmetic in the reference's operation order (phase boundaries depend on it)."""
+    offf, durf, ph = _f32_phase_arrays(gait_id, phase)
+    p = ph - offf
+    p = np.where(p < 0, p + np.float32(1.0), p)
+    return np.where(p > durf, np.float32(0.0), p / durf)
 
 
 def swing_state(gait_id, phase) -> np.ndarray:
     """Gait.getSwingState (Gait.py:46-67): swing progress in [0,1], 0 while in stance."""
-    off, dur = gait_arrays(gait_id)
-    offf, durf = off / N_SEGMENT, dur / N_SEGMENT
+    offf, durf, ph = _f32_phase_arrays(gait_id, phase)
     sw_off = offf + durf
-    sw_off = np.where(sw_off > 1, sw_off - 1.0, sw_off)
-    sw_dur = 1.0 - durf
-    p = np.asarray(phase, dtype=np.float64)[..., None] - sw_off
-    p = np.where(p < 0, p + 1.0, p)
-    safe = np.where(sw_dur == 0, 1.0, sw_dur)
-    return np.where((p > sw_dur) | (sw_dur == 0), 0.0, p / safe)
+    sw_off = np.where(sw_off > 1, sw_off - np.float32(1.0), sw_off)
+    sw_dur = np.float32(1.0) - durf
+    p = ph - sw_off
+    p = np.where(p < 0, p + np.float32(1.0), p)
+    safe = np.where(sw_dur == 0, np.float32(1.0), sw_dur)
+    return np.where((p > sw_dur) | (sw_dur == 0), np.float32(0.0), p / safe)

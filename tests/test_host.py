@@ -1,0 +1,89 @@
+"""CPU tests of the host side: record layout vs the C header, gait tables vs the reference's
+own Gait.py (golden fixture), the C-ABI library's exports, and loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from rl_mpc_locomotion_b200 import _lib, gait, records, synth
+from rl_mpc_locomotion_b200.robots import ROBOTS, RobotType, params_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mpc_b200.h")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_record_offsets_match_header():
+    txt = open(HEADER).read()
+    for name, val in re.findall(r"#define\s+MPC_REC_(\w+)\s+(\d+)", txt):
+        assert getattr(records, f"REC_{name}") == int(val), name
+    assert records.rec_stride(10) == 96 and records.rec_stride(16) == 120
+    assert int(re.search(r"#define\s+MPC_ROBOT_PARAMS_STRIDE\s+(\d+)", txt).group(1)) == records.ROBOT_PARAMS_STRIDE
+
+
+def test_pack_unpack_roundtrip():
+    rec, rt, params, _ = synth.make_batch(5, 10, seed=9)
+    kw = records.unpack_record(rec[2], 10)
+    table = kw.pop("foot_contact_states")
+    again = records.pack_records(10, foot_contact_states=table, **kw)
+    assert np.array_equal(again[0], rec[2])
+
+
+def test_gait_tables_match_reference_gait_py():
+    g = np.load(os.path.join(GOLD, "gait_golden.npz"))
+    for gid in gait.GAITS:
+        for tick in range(40):
+            it, phase = gait.gait_iteration(tick, 2)
+            assert np.array_equal(gait.mpc_table(gid, it, 10), g[f"table_{gid}"][tick]), (gid, tick)
+            assert np.allclose(gait.contact_state(gid, phase), g[f"contact_{gid}"][tick], atol=1e-6)
+            assert np.allclose(gait.swing_state(gid, phase), g[f"swing_{gid}"][tick], atol=1e-6)
+    # horizon 16 cycles the 10-segment gait
+    t16 = gait.mpc_table(0, 0.5, 16)
+    assert np.array_equal(t16[:40], gait.mpc_table(0, 0.5, 10)) and np.array_equal(t16[40:64], t16[0:24])
+
+
+def test_robot_table_matches_reference_constants():
+    a = ROBOTS[RobotType.ALIENGO]
+    assert abs(a.mass - 18.082) < 1e-12 and a.body_height == 0.35 and a.friction == 0.4
+    assert params_table().shape == (3, 12)
+    assert np.allclose(ROBOTS[RobotType.A1].inertia_diag, (0.17, 0.57, 0.64))
+    assert np.allclose(ROBOTS[RobotType.GO1].hip_location(3), (-0.1881, -0.04675, 0))
+
+
+def test_library_exports_every_declared_symbol():
+    txt = open(HEADER).read()
+    declared = set(re.findall(r"\b(mpc_b200_\w+)\s*\(", txt))
+    assert declared == set(_lib.EXPORTS)
+    lib = _lib.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert b"sm_100a" in lib.mpc_b200_version()
+    s = _lib.default_settings()
+    assert (s.horizon, s.max_iter, s.check_every, s.scaling_iters, s.polish) == (10, 4000, 25, 10, 1)
+    assert (s.rho, s.sigma, s.relax, s.eps_abs, s.delta) == (0.1, 1e-6, 1.6, 1e-3, 1e-6)
+    info = _lib.kernel_info(10)
+    assert info["smem_bytes"] < 227 * 1024 and info["robots_per_cta"] == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly (never route through the oracle)."""
+    if _lib.lib().mpc_b200_device_count() > 0:
+        pytest.skip("GPU present")
+    from rl_mpc_locomotion_b200.batched import solve_host
+    rec, rt, params, _ = synth.make_batch(2, 10, seed=0)
+    with pytest.raises(_lib.MpcB200Error, match="no CUDA device"):
+        solve_host(rec, 10, robot_params=params, robot_type=rt)
+    with pytest.raises(_lib.MpcB200Error):
+        _lib.check(_lib.lib().mpc_b200_solve_batch(C.byref(_lib.default_settings(horizon=12)), None, None, None,
+                                                   0, None, None, None, None, None, None), "bad horizon")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "rl_mpc_locomotion_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", "") or f in ("synth.py",), f
