@@ -1,6 +1,6 @@
 // mpc_b200.cu — sm_100a kernels + the C-ABI of include/mpc_b200.h.
 //
-// One CTA = one warp = one robot.  The hardware block scheduler load-balances the
+// One CTA = MPC_NL threads (two warps) = one robot.  The hardware block scheduler load-balances the
 // variable per-robot iteration counts (OSQP terminates after 50..300 iterations depending
 // on the state).  The robot's 384-byte problem record is staged HBM -> shared memory with
 // one TMA bulk copy (cp.async.bulk, mbarrier completion); everything else the solver
@@ -62,6 +62,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+#ifndef MPC_MIN_CTAS
+#define MPC_MIN_CTAS 8   // resident robots per SM the register allocation is tuned for
+#endif
+
 template <int H>
 struct KernelCfg {
   using D = mpc::Dims<H>;
@@ -75,7 +79,7 @@ struct KernelCfg {
 };
 
 template <int H>
-__global__ void __launch_bounds__(32, 1)
+__global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
 mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                  const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
                  int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
@@ -100,7 +104,7 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
   const int type = robot_type ? robot_type[robot] : 0;
   if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
   mpc::fill_tables<H>(sm, prm.dt, lane);
-  __syncwarp();
+  WSYNC();
   mbar_wait(bar, 0);
 
   constexpr int dbg_stride = 12 * H + 144 * H * H + 12 * H + 20 * H + 1;
@@ -170,7 +174,7 @@ int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
   if (n <= 0) return MPC_B200_OK;
-  mpc_solve_kernel<H><<<n, 32, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status, resid,
+  mpc_solve_kernel<H><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status, resid,
                                                        info, dbg);
   CK(cudaGetLastError());
   return MPC_B200_OK;
@@ -246,7 +250,7 @@ int mpc_b200_device_count(void) {
 int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int* regs_per_thread) {
   if (horizon != 10 && horizon != 16) return MPC_B200_EINVAL;
   if (smem_bytes) *smem_bytes = horizon == 10 ? KernelCfg<10>::SMEM_BYTES : KernelCfg<16>::SMEM_BYTES;
-  if (robots_per_cta) *robots_per_cta = 1;
+  if (robots_per_cta) *robots_per_cta = 1;  /* MPC_NL threads cooperate on it */
   if (regs_per_thread) {
     *regs_per_thread = -1;
     cudaFuncAttributes a;

@@ -36,6 +36,8 @@
 
 namespace mpc {
 
+constexpr int NL = MPC_NL;  // threads per robot (1 or 2 warps), see warp_prog.h
+
 struct SolveParams {
   int max_iter;         // osqp MAX_ITER 4000
   int check_every;      // osqp CHECK_TERMINATION 25 (== adaptive_rho_interval, mpc_osqp.cc:710)
@@ -61,14 +63,15 @@ constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
 
 template <int H>
 struct Dims {
+  static constexpr int NL = MPC_NL;              // lanes (threads) cooperating on one robot
   static constexpr int NV = 12 * H;             // variables
   static constexpr int NLS = 4 * H;             // (step, leg) pairs
-  static constexpr int NSLOT = (NLS + 31) / 32; // leg-steps per lane
+  static constexpr int NSLOT = (NLS + NL - 1) / NL; // leg-steps per lane
   static constexpr int NW = 6 * H;              // wrench-space dimension
-  static constexpr int NWS = (NW + 31) / 32;
-  static constexpr int NVS = (NV + 31) / 32;
+  static constexpr int NWS = (NW + NL - 1) / NL;
+  static constexpr int NVS = (NV + NL - 1) / NL;
   static constexpr int NP = (NW + 1) / 2;             // row pairs (i, NW-1-i) of the triangle
-  static constexpr int NRS = 2 * ((NP + 31) / 32);    // triangle rows owned per lane
+  static constexpr int NRS = 2 * ((NP + NL - 1) / NL);  // (unused) triangle rows per lane
   static constexpr int NTRI = NW * (NW - 1) / 2;      // packed strictly-lower triangle
   // shared-memory layout (doubles)
   static constexpr int OFF_WP = 0;                       // [NTRI] Hm -> L -> W = L^-1, row-packed
@@ -100,7 +103,7 @@ MPC_LANEFN int tri(int i) { return (i * (i - 1)) >> 1; }
 // Rows of an n x n triangle owned by `lane`: rows are paired (p, n-1-p) so that every lane
 // carries the same number of elements (n-1) per pair.
 MPC_LANEFN int rowmap(int lane, int n, int r) {
-  const int p = lane + 32 * (r >> 1);
+  const int p = lane + NL * (r >> 1);
   if (p >= ((n + 1) >> 1)) return -1;
   if (r & 1) {
     const int q = n - 1 - p;
@@ -192,7 +195,7 @@ MPC_FN void fill_tables(double* sm, double dt
 ) {
   using D = Dims<H>;
   LANES_BEGIN
-  for (int e = lane; e < H * H; e += 32) {
+  for (int e = lane; e < H * H; e += NL) {
     const int i = e / H, j = e % H;
     const int k0 = i > j ? i : j;
     double g = 0;
@@ -372,7 +375,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   }
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    const int j = lane + 32 * s;
+    const int j = lane + NL * s;
     _(valid)[s] = j < D::NLS;
     _(cj)[s] = _(valid)[s] ? (double)rec[MPC_REC_CONTACT + j] : 0.0;
   }
@@ -427,7 +430,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   WSYNC();
   // acc_j = sum_{k>=j} c_{k-j} a_k + b_k ; balanced (rows 0..2 divided by s) -> vt
   LANES_BEGIN
-  for (int i = lane; i < NW; i += 32) {
+  for (int i = lane; i < NW; i += NL) {
     const int j = i / 6, c = i % 6;
     double acc = 0;
     for (int k = j; k < H; ++k) acc += (dt * dt * ((k - j) + 0.5)) * vg[6 * k + c] + vw[6 * k + c];
@@ -439,7 +442,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   LANES_BEGIN
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    const int j = lane + 32 * s;
+    const int j = lane + NL * s;
     const int k = (j >> 2) < H ? (j >> 2) : 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -457,7 +460,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       _(yv)[s][r] = 0.0;
     }
   }
-  for (int v = lane; v < NV; v += 32) Dsm[v] = 1.0;
+  for (int v = lane; v < NV; v += NL) Dsm[v] = 1.0;
   LANES_END
   WSYNC();
   if (dbg_out) {  // unscaled q for builder tests
@@ -466,7 +469,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s])
 #pragma unroll
-        for (int a = 0; a < 3; ++a) dbg_out[3 * (lane + 32 * s) + a] = _(qb)[s][a];
+        for (int a = 0; a < 3; ++a) dbg_out[3 * (lane + NL * s) + a] = _(qb)[s][a];
     LANES_END
   }
 
@@ -476,8 +479,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   double* const G2 = Wp + 144;
   double* const Y1 = Wp + 288;  // Q1' Wb' (6x12)
   LANES_BEGIN
-  for (int e = lane; e < 36; e += 32) q1s[e] = Q1at(e / 6, e % 6);
-  for (int e = lane; e < 72; e += 32) {
+  for (int e = lane; e < 36; e += NL) q1s[e] = Q1at(e / 6, e % 6);
+  for (int e = lane; e < 72; e += NL) {
     const int c = e / 12, b = e % 12;
     double y1 = 0;
     if (c < 3) {
@@ -491,7 +494,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   LANES_END
   WSYNC();
   LANES_BEGIN
-  for (int e = lane; e < 144; e += 32) {
+  for (int e = lane; e < 144; e += NL) {
     const int a = e / 12, b = e % 12;
     double g1 = 0, g2 = 0;
 #pragma unroll
@@ -506,7 +509,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   WSYNC();
   if (dbg_out) {  // dense P (unscaled) for builder tests: dbg_out[NV + i*NV + v]
     LANES_BEGIN
-    for (int v = lane; v < NV; v += 32) {
+    for (int v = lane; v < NV; v += NL) {
       const int k2 = v / 12, b = v % 12;
       for (int k = 0; k < H; ++k)
         for (int a = 0; a < 12; ++a) {
@@ -522,7 +525,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   // column inf-norms of (D P D) WITHOUT the c factor -> vecA   (scaling.c:30-43, lin_alg.c:358)
   auto col_norms_P = [&]() {
     LANES_BEGIN
-    for (int v = lane; v < NV; v += 32) {
+    for (int v = lane; v < NV; v += NL) {
       const int k2 = v / 12, b = v % 12;
       double g1[12], g2[12];
 #pragma unroll
@@ -554,7 +557,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     double qmax = 0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      const int j = lane + 32 * s;
+      const int j = lane + NL * s;
       if (_(valid)[s]) {
         const double* E = _(Ev)[s];
         const double* Dd = _(Dv)[s];
@@ -587,7 +590,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     col_norms_P();
     LANES_BEGIN
     double ssum = 0, qmax = 0;
-    for (int v = lane; v < NV; v += 32) ssum += cscale * vecA[v];
+    for (int v = lane; v < NV; v += NL) ssum += cscale * vecA[v];
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s])
@@ -615,7 +618,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s]) {
-        const int j = lane + 32 * s;
+        const int j = lane + NL * s;
 #pragma unroll
         for (int a = 0; a < 3; ++a) dbg_out[NV + NV * NV + 3 * j + a] = _(Dv)[s][a];
 #pragma unroll
@@ -649,13 +652,13 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 
   // dense Cholesky (left-looking) of the leading n x n block held as: strictly-lower triangle in
   // Wp (row-packed), diagonal in dinv[].  On exit Wp holds L (strictly lower) and dinv[i] = 1/L_ii.
-  // Row i is owned by lane i % 32; inner loops have warp-uniform trip counts (j).
+  // Row i is owned by lane i % NL; inner loops have warp-uniform trip counts (j).
   auto cholesky = [&](int n) {
     for (int j = 0; j < n; ++j) {
       const double* rowj = Wp + tri(j);
       LANES_BEGIN
       // first owned row >= j
-      for (int i = j + ((lane - j) & 31); i < n; i += 32) {
+      for (int i = j + ((lane - j) & (NL - 1)); i < n; i += NL) {
         double* rowi = Wp + tri(i);
         double a0 = (i == j) ? dinv[j] : rowi[j], a1 = 0.0;
         int k = 0;
@@ -673,7 +676,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       WSYNC();
       LANES_BEGIN
       const double inv = dinv[j];
-      for (int i = j + 1 + ((lane - j - 1) & 31); i < n; i += 32) Wp[tri(i) + j] *= inv;
+      for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) Wp[tri(i) + j] *= inv;
       LANES_END
       WSYNC();
     }
@@ -686,12 +689,12 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     for (int j = n - 2; j >= 0; --j) {
       double* const buf = colb + (j & 1) * NW;
       LANES_BEGIN
-      for (int i = j + 1 + ((lane - j - 1) & 31); i < n; i += 32) buf[i] = Wp[tri(i) + j];
+      for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) buf[i] = Wp[tri(i) + j];
       LANES_END
       WSYNC();
       LANES_BEGIN
       const double dj = dinv[j];
-      for (int i = j + 1 + ((lane - j - 1) & 31); i < n; i += 32) {
+      for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) {
         double* rowi = Wp + tri(i);
         double a0 = dinv[i] * buf[i], a1 = 0.0;
         int k = j + 1;
@@ -715,7 +718,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_BEGIN
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      const int j = lane + 32 * s;
+      const int j = lane + NL * s;
       if (_(valid)[s]) {
         const double* E = _(Ev)[s];
         const double* Dd = _(Dv)[s];
@@ -776,7 +779,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     WSYNC();
     // Hm = blkdiag(Finv) + 2c (Gamma (x) Q1' + N (x) Q2')  (strictly-lower rows + diagonal)
     LANES_BEGIN
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double* const row = Wp + tri(i);
       const double* q1r = q1s + c * 6;
@@ -804,7 +807,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (_(valid)[s]) {
-        const int j = lane + 32 * s;
+        const int j = lane + NL * s;
         double sv[3];
         mul3sym(_(di)[s], _(tmp3)[s], sv);
 #pragma unroll
@@ -817,7 +820,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN  // t = U s
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double t = 0;
 #pragma unroll
@@ -827,7 +830,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN  // g = F^-1 t
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double g = 0;
 #pragma unroll
@@ -837,7 +840,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const double* rowi = Wp + tri(i);
       double a0 = dinv[i] * vg[i], a1 = 0.0;
       int k = 0;
@@ -852,7 +855,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN  // w = W^T y (column walk: W[i][c] contiguous across lanes for a fixed row i)
-    for (int c = lane; c < NW; c += 32) {
+    for (int c = lane; c < NW; c += NL) {
       double a0 = dinv[c] * vw[c], a1 = 0.0;
       int i = c + 1;
       const double* p = Wp + tri(i) + c;     // &W[i][c]; next row is i further on
@@ -868,7 +871,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN  // v = g - F^-1 w  -> vecB (NW <= NV)
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double v = vg[i];
 #pragma unroll
@@ -881,7 +884,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (_(valid)[s]) {
-        const int j = lane + 32 * s;
+        const int j = lane + NL * s;
         const int k = j >> 2;
         double u[3], du[3];
 #pragma unroll
@@ -906,14 +909,14 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s]) {
-        const int j = lane + 32 * s;
+        const int j = lane + NL * s;
 #pragma unroll
         for (int a = 0; a < 3; ++a) vecA[3 * j + a] = _(Dv)[s][a] * _(tmp3)[s][a];
       }
     LANES_END
     WSYNC();
     LANES_BEGIN
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double t = 0;
 #pragma unroll
@@ -923,7 +926,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double a1 = 0;
 #pragma unroll
@@ -934,7 +937,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
     LANES_BEGIN
-    for (int i = lane; i < NW; i += 32) {
+    for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
       double o = 0;
       for (int k2 = 0; k2 < H; ++k2) o += gam[k * H + k2] * vg[6 * k2 + c] + nnm[k * H + k2] * vw[6 * k2 + c];
@@ -946,7 +949,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s]) {
-        const int j = lane + 32 * s;
+        const int j = lane + NL * s;
         const int k = j >> 2;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -1250,7 +1253,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       for (int s = 0; s < NS; ++s) {
         _(foff)[s] = o;
         if (_(valid)[s]) {
-          const int j = lane + 32 * s;
+          const int j = lane + NL * s;
           const int k = j >> 2;
           for (int p = _(rk)[s]; p < 3; ++p) {
             const double* nu = _(Yb)[s][p];
@@ -1269,7 +1272,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         if (_(valid)[s]) {
-          const int j = lane + 32 * s;
+          const int j = lane + NL * s;
           const int k = j >> 2;
           int f = _(foff)[s];
           for (int p = _(rk)[s]; p < 3; ++p, ++f) {
@@ -1297,7 +1300,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       WSYNC();
       // M = K_f + delta*I: wrench part (strictly-lower rows in Wp, diagonal in dinv)
       LANES_BEGIN
-      for (int f = lane; f < nf; f += 32) {
+      for (int f = lane; f < nf; f += NL) {
         double m[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) m[c] = Mf[6 * f + c];
@@ -1347,7 +1350,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int j = 0; j < nf; ++j) {
           LANES_BEGIN
           const double yj = pv[j] * dinv[j];
-          for (int i = j + 1 + lane; i < nf; i += 32) pv[i] -= Wp[tri(i) + j] * yj;
+          for (int i = j + 1 + lane; i < nf; i += NL) pv[i] -= Wp[tri(i) + j] * yj;
           LANES_END
           WSYNC();
           LANES_BEGIN
@@ -1359,7 +1362,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
           LANES_BEGIN
           const double xj = pv[j] * dinv[j];
           const double* rowj = Wp + tri(j);
-          for (int i = lane; i < j; i += 32) pv[i] -= rowj[i] * xj;
+          for (int i = lane; i < j; i += NL) pv[i] -= rowj[i] * xj;
           LANES_END
           WSYNC();
           LANES_BEGIN
@@ -1378,7 +1381,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       WSYNC();
       tri_solve();
       LANES_BEGIN
-      for (int f = lane; f < nf; f += 32) {
+      for (int f = lane; f < nf; f += NL) {
         pxi[f] = pv[f];
         pxi0[f] = pv[f];
       }
@@ -1388,12 +1391,12 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       // which is algebraically xi <- xi_0 + delta * M^-1 xi (no copy of K_f needed)
       for (int itr = 0; itr < prm.polish_refine; ++itr) {
         LANES_BEGIN
-        for (int f = lane; f < nf; f += 32) pv[f] = pxi[f];
+        for (int f = lane; f < nf; f += NL) pv[f] = pxi[f];
         LANES_END
         WSYNC();
         tri_solve();
         LANES_BEGIN
-        for (int f = lane; f < nf; f += 32) pxi[f] = pxi0[f] + prm.delta * pv[f];
+        for (int f = lane; f < nf; f += NL) pxi[f] = pxi0[f] + prm.delta * pv[f];
         LANES_END
         WSYNC();
       }
@@ -1421,7 +1424,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       for (int s = 0; s < NS; ++s)
         if (_(valid)[s])
 #pragma unroll
-          for (int a = 0; a < 3; ++a) Dsm[3 * (lane + 32 * s) + a] = _(Dv)[s][a];
+          for (int a = 0; a < 3; ++a) Dsm[3 * (lane + NL * s) + a] = _(Dv)[s][a];
       LANES_END
       WSYNC();
       apply_P();
@@ -1526,7 +1529,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     if (_(valid)[s]) {
-      const int j = lane + 32 * s;
+      const int j = lane + NL * s;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float f = (float)(-_(Dv)[s][a] * _(xv)[s][a]);

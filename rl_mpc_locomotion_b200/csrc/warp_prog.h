@@ -1,20 +1,26 @@
-// warp_prog.h — the "warp program" dialect the solver is written in.
+// warp_prog.h — the "lane program" dialect the solver is written in.
 //
-// The solver (mpc_warp_solver.cuh) is one warp-synchronous program: 32 lanes own one
-// robot's QP end to end.  It is written as a sequence of lane-local blocks
-// (LANES_BEGIN ... LANES_END) separated by warp-level exchange points (shared-memory
-// hand-offs + WSYNC, or the W* collectives below).
+// The solver (mpc_warp_solver.cuh) is one lock-step program executed by MPC_NL lanes that own
+// one robot's QP end to end (MPC_NL = 64: two warps = one CTA per robot; 32: one warp).  It
+// is written as a sequence of lane-local blocks (LANES_BEGIN ... LANES_END) separated by
+// exchange points (shared-memory hand-offs + WSYNC, or the W* collectives below).
 //
 //  * Under nvcc (the product) LANES_BEGIN/END are plain braces: every thread executes the
 //    block once with its own `lane`, per-lane variables are registers, collectives are
-//    __shfl_xor_sync butterflies, WSYNC is __syncwarp().
+//    __shfl_xor_sync butterflies (+ one shared-memory hop between the two warps), WSYNC is
+//    __syncwarp() / __syncthreads().
 //  * With -DMPC_EMULATE (g++, tests/warp_emu only — a development and CI aid so that the
 //    kernel logic can be exercised without a GPU; it is NOT shipped, not importable from
 //    the package and never used by bench.py or the public API) LANES_BEGIN/END become a
-//    `for lane in 0..31` loop, per-lane variables become arrays of 32 and collectives
-//    become loops over that array.  Because every cross-lane hand-off happens only at
-//    the block boundaries, the sequential emulation is exact.
+//    `for lane in 0..MPC_NL-1` loop, per-lane variables become arrays and collectives become
+//    loops over that array.  Because every cross-lane hand-off happens only at the block
+//    boundaries, the sequential emulation is exact.
 #pragma once
+
+#ifndef MPC_NL
+#define MPC_NL 64
+#endif
+static_assert(MPC_NL == 32 || MPC_NL == 64, "MPC_NL must be 32 or 64");
 
 #if defined(__CUDACC__) && !defined(MPC_EMULATE)
 // ------------------------------------------------------------------ device build
@@ -25,47 +31,78 @@
 #define PER_LANE(T, name) T name
 #define PER_LANE_ARR(T, name, dims) T name dims
 #define _(name) name
+#if MPC_NL == 32
 #define WSYNC() __syncwarp()
+#else
+#define WSYNC() __syncthreads()
+#endif
 
 namespace mpcw {
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
+// one 8-slot exchange buffer per CTA (one robot per CTA) for the cross-warp hop
+__device__ __forceinline__ double* xbuf() {
+  __shared__ double buf[8];
+  return buf;
+}
 __device__ __forceinline__ double wmax(double v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor_d(v, m));
+#if MPC_NL == 64
+  double* b = xbuf();
+  if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = fmax(b[0], b[1]);
+  __syncthreads();
+#endif
   return v;
 }
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
+#if MPC_NL == 64
+  double* b = xbuf();
+  if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = b[0] + b[1];
+  __syncthreads();
+#endif
   return v;
 }
 __device__ __forceinline__ int wsum_i(int v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+#if MPC_NL == 64
+  int* b = reinterpret_cast<int*>(xbuf() + 4);
+  if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = b[0] + b[1];
+  __syncthreads();
+#endif
   return v;
 }
-__device__ __forceinline__ int wor_i(int v) {
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
-  return v;
-}
-// exclusive prefix sum of an int over the warp (lane order)
+// exclusive prefix sum of an int over the lanes (lane order)
 __device__ __forceinline__ int wexscan_i(int v, int lane) {
   int s = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int t = __shfl_up_sync(0xffffffffu, s, d);
-    if (lane >= d) s += t;
+    if ((lane & 31) >= d) s += t;
   }
+#if MPC_NL == 64
+  int* b = reinterpret_cast<int*>(xbuf() + 6);
+  if (lane == 31) b[0] = s;  // total of warp 0
+  __syncthreads();
+  if (lane >= 32) s += b[0];
+  __syncthreads();
+#endif
   return s - v;
 }
 }  // namespace mpcw
 #define WMAX(v) mpcw::wmax(v)
 #define WSUM(v) mpcw::wsum(v)
 #define WSUM_I(v) mpcw::wsum_i(v)
-#define WOR_I(v) mpcw::wor_i(v)
 // dst (per-lane int) = exclusive scan of src (per-lane int)
 #define WEXSCAN_I(dst, src) dst = mpcw::wexscan_i(src, lane)
 
@@ -74,43 +111,42 @@ __device__ __forceinline__ int wexscan_i(int v, int lane) {
 #include <cmath>
 #define MPC_FN inline
 #define MPC_LANEFN inline
-#define LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define LANES_BEGIN for (int lane = 0; lane < MPC_NL; ++lane) {
 #define LANES_END }
-#define PER_LANE(T, name) T name[32]
-#define PER_LANE_ARR(T, name, dims) T name[32] dims
+#define PER_LANE(T, name) T name[MPC_NL]
+#define PER_LANE_ARR(T, name, dims) T name[MPC_NL] dims
 #define _(name) name[lane]
 #define WSYNC() ((void)0)
 
 namespace mpcw {
-inline double wmax(const double (&v)[32]) {
+inline double wmax(const double (&v)[MPC_NL]) {
   double m = v[0];
-  for (int i = 1; i < 32; ++i) m = std::fmax(m, v[i]);
+  for (int i = 1; i < MPC_NL; ++i) m = std::fmax(m, v[i]);
   return m;
 }
-inline double wsum(const double (&v)[32]) {
-  // same butterfly order as the device build so the rounding matches
-  double t[32];
-  for (int i = 0; i < 32; ++i) t[i] = v[i];
-  for (int m = 16; m > 0; m >>= 1) {
-    double u[32];
-    for (int i = 0; i < 32; ++i) u[i] = t[i] + t[i ^ m];
-    for (int i = 0; i < 32; ++i) t[i] = u[i];
+inline double wsum(const double (&v)[MPC_NL]) {
+  // same association order as the device build: a 32-lane butterfly per warp, then warp0+warp1
+  double tot[MPC_NL / 32];
+  for (int w = 0; w < MPC_NL / 32; ++w) {
+    double t[32];
+    for (int i = 0; i < 32; ++i) t[i] = v[32 * w + i];
+    for (int m = 16; m > 0; m >>= 1) {
+      double u[32];
+      for (int i = 0; i < 32; ++i) u[i] = t[i] + t[i ^ m];
+      for (int i = 0; i < 32; ++i) t[i] = u[i];
+    }
+    tot[w] = t[0];
   }
-  return t[0];
+  return MPC_NL == 64 ? tot[0] + tot[MPC_NL / 32 - 1] : tot[0];
 }
-inline int wsum_i(const int (&v)[32]) {
+inline int wsum_i(const int (&v)[MPC_NL]) {
   int s = 0;
-  for (int i = 0; i < 32; ++i) s += v[i];
+  for (int i = 0; i < MPC_NL; ++i) s += v[i];
   return s;
 }
-inline int wor_i(const int (&v)[32]) {
+inline void wexscan_i(int (&dst)[MPC_NL], const int (&src)[MPC_NL]) {
   int s = 0;
-  for (int i = 0; i < 32; ++i) s |= v[i];
-  return s;
-}
-inline void wexscan_i(int (&dst)[32], const int (&src)[32]) {
-  int s = 0;
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < MPC_NL; ++i) {
     int v = src[i];
     dst[i] = s;
     s += v;
@@ -120,6 +156,5 @@ inline void wexscan_i(int (&dst)[32], const int (&src)[32]) {
 #define WMAX(v) mpcw::wmax(v)
 #define WSUM(v) mpcw::wsum(v)
 #define WSUM_I(v) mpcw::wsum_i(v)
-#define WOR_I(v) mpcw::wor_i(v)
 #define WEXSCAN_I(dst, src) mpcw::wexscan_i(dst, src)
 #endif
