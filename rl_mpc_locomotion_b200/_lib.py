@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+LIB_PATH = os.environ.get("MPC_B200_LIB", os.path.join(_HERE, "libmpc_b200.so"))  # env override: A/B builds
 
 MODE_OSQP, MODE_FIXED = 0, 1
 STATUS_SOLVED, STATUS_MAX_ITER = 1, -2

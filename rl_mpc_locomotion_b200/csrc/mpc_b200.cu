@@ -63,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 #ifndef MPC_MIN_CTAS
-#define MPC_MIN_CTAS 8   // resident robots per SM the register allocation is tuned for
+#define MPC_MIN_CTAS 6   // resident robots per SM the register allocation is tuned for (168 regs: no hot-loop spills)
 #endif
 
 template <int H>

@@ -544,7 +544,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         }
       }
       // diagonal entry carries + alpha (P_vv >= 0, so |P_vv + alpha| only grows the max)
-      const double pd = gam[k2 * H + k2] * g1[b] + nnm[k2 * H + k2] * g2[b] + alpha;
+      const double pd = 2.0 * (gam[k2 * H + k2] * G1[b * 12 + b] + nnm[k2 * H + k2] * G2[b * 12 + b]) + alpha;
       vecA[v] = fmax(fmax(m0, m1), Dsm[v] * pd) * Dsm[v];
     }
     LANES_END
@@ -842,31 +842,45 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
     for (int i = lane; i < NW; i += NL) {
       const double* rowi = Wp + tri(i);
-      double a0 = dinv[i] * vg[i], a1 = 0.0;
+      double a0 = dinv[i] * vg[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int k = 0;
-#pragma unroll 2
-      for (; k + 1 < i; k += 2) {
-        a0 += rowi[k] * vg[k];
-        a1 += rowi[k + 1] * vg[k + 1];
+      for (; k + 3 < i; k += 4) {
+        const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+        const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
+        a0 += rowi[k] * g01.x;
+        a1 += rowi[k + 1] * g01.y;
+        a2 += rowi[k + 2] * g23.x;
+        a3 += rowi[k + 3] * g23.y;
       }
-      if (k < i) a0 += rowi[k] * vg[k];
-      vw[i] = a0 + a1;
+      for (; k < i; ++k) a0 += rowi[k] * vg[k];
+      vw[i] = (a0 + a1) + (a2 + a3);
     }
     LANES_END
     WSYNC();
     LANES_BEGIN  // w = W^T y (column walk: W[i][c] contiguous across lanes for a fixed row i)
     for (int c = lane; c < NW; c += NL) {
-      double a0 = dinv[c] * vw[c], a1 = 0.0;
+      double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int i = c + 1;
-      const double* p = Wp + tri(i) + c;     // &W[i][c]; next row is i further on
-#pragma unroll 2
-      for (; i + 1 < NW; i += 2) {
+      const double* p = Wp + tri(i) + c;     // &W[i][c]; W[i+1][c] = p[i]
+      if ((i & 1) && i < NW) {               // align i to even so that vw pairs are 16-byte aligned
         a0 += p[0] * vw[i];
-        a1 += p[i] * vw[i + 1];
-        p += 2 * i + 1;
+        p += i;
+        ++i;
       }
-      if (i < NW) a0 += p[0] * vw[i];
-      vt[c] = a0 + a1;
+      for (; i + 3 < NW; i += 4) {
+        const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
+        const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
+        a0 += p[0] * y01.x;
+        a1 += p[i] * y01.y;
+        a2 += p[2 * i + 1] * y23.x;
+        a3 += p[3 * i + 3] * y23.y;
+        p += 4 * i + 6;
+      }
+      for (; i < NW; ++i) {
+        a0 += p[0] * vw[i];
+        p += i;
+      }
+      vt[c] = (a0 + a1) + (a2 + a3);
     }
     LANES_END
     WSYNC();
@@ -974,10 +988,9 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     const double* E = _(Ev)[s];
     const bool eq = (hi_of(E, _(cj)[s], 4) - lo_of(E, _(cj)[s], 4) < kRhoTol);
     _(rhoj)[s] = eq ? kRhoEqFactor * rho : rho;
-    _(tmp3)[s][0] = eq ? 1.0 : 0.0;  // remember the type in tmp (re-derived below)
   }
   LANES_END
-  factor(prm.sigma);
+  bool need_factor = true;   // factor() has ONE call site (top of the loop): one register allocation
 
   // ------------------------------------------------------------------ S4: ADMM
   const double ar = prm.relax, sigma = prm.sigma;
@@ -989,6 +1002,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   PER_LANE_ARR(double, nrm, [14]);
   const int max_iter = prm.fixed_iters > 0 ? prm.fixed_iters : prm.max_iter;
   for (iter = 1; iter <= max_iter; ++iter) {
+    if (need_factor) {
+      factor(prm.sigma);
+      need_factor = false;
+    }
     LANES_BEGIN  // rhs = sigma x - q + A^T (rho z - y)      (auxil.c:149-162)
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -1106,7 +1123,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
           _(rhoj)[s] = eq ? kRhoEqFactor * rho : rho;
         }
         LANES_END
-        factor(prm.sigma);
+        need_factor = true;
       }
     }
   }

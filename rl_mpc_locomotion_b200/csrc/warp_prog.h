@@ -109,6 +109,9 @@ __device__ __forceinline__ int wexscan_i(int v, int lane) {
 #else
 // ------------------------------------------------------------------ emulation build
 #include <cmath>
+struct double2 {
+  double x, y;
+};
 #define MPC_FN inline
 #define MPC_LANEFN inline
 #define LANES_BEGIN for (int lane = 0; lane < MPC_NL; ++lane) {
