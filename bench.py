@@ -18,7 +18,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -46,45 +45,50 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle sampling DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md), through
+    NVML in a polling thread (nvidia-smi -lms is too coarse for a ~0.1 s region)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
-
-    def start(self):
+        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.t.join()
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                "power_w_max": max((r[2] for r in self.rows), default=None), "reasons": reasons,
                 "samples": len(sm)}
 
 
@@ -96,19 +100,24 @@ def _oracle_worker(args):
     return time.perf_counter() - t0, int((st == 1).sum())
 
 
-def cpu_reference_rate(rec, rt, params, h, cores, passes=1, mode=0):
+def cpu_reference_rate(rec, rt, params, h, cores, per_worker=192, mode=0):
     """The reference's CPU path (oracle = builder restatement + UNMODIFIED reference OSQP) on
-    `cores` host processes (OSQP installs a process-global SIGINT handler: processes, not threads)."""
+    `cores` host processes (OSQP installs a process-global SIGINT handler: processes, not
+    threads).  Every worker solves `per_worker` records taken cyclically from the workload
+    batch (~0.5-1 s of work each); pool start-up and a warm-up call are outside the clock."""
     import multiprocessing as mp
-    chunks = [(rec[i::cores], h, params, rt[i::cores], mode) for i in range(cores)]
+    n = len(rec)
+    chunks = []
+    for w in range(cores):
+        idx = (np.arange(per_worker) * cores + w) % n
+        chunks.append((rec[idx], h, params, rt[idx], mode))
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_oracle_worker, [(rec[:8], h, params, rt[:8], mode)] * cores)   # warm the workers
+        pool.map(_oracle_worker, [(rec[:4], h, params, rt[:4], mode)] * cores)   # warm the workers
         t0 = time.perf_counter()
-        for _ in range(passes):
-            pool.map(_oracle_worker, chunks)
+        pool.map(_oracle_worker, chunks, chunksize=1)
         wall = time.perf_counter() - t0
-    return passes * len(rec) / wall, wall
+    return cores * per_worker / wall, wall, cores * per_worker
 
 
 def main():
@@ -137,25 +146,22 @@ def main():
            "solver_mode": "osqp-faithful (reference settings, fp64)" if args.mode == "osqp"
            else f"fixed {args.admm_iters} ADMM iterations, no polish",
            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"robots sharded x{world}"}
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = min(len(rec), 1024)
-        for _ in range(max(0, min(args.warmup, 1))):
-            cpu_reference_rate(rec[:64], rt[:64], params, h, cores)
-        rates = []
-        for _ in range(max(1, args.steps)):
-            r, wall = cpu_reference_rate(rec[:sample], rt[:sample], params, h, cores)
+        rates, sample = [], 0
+        for _ in range(max(1, min(args.steps, 5))):
+            r, wall, sample = cpu_reference_rate(rec, rt, params, h, cores)
             rates.append(r)
         v = float(np.mean(rates))
         line = {"impl": "reference", "metric": "QP solves/sec", "value": v, "unit": "solves/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                 "sample": f"{sample} records of the workload per step; QP builder = Eigen-free "
+                                 "sample": f"{sample} records (cyclic draw from the workload) per step; QP builder = Eigen-free "
                                            "restatement of mpc_osqp.cc, solver = the reference's vendored OSQP "
                                            "0.6.0 compiled unmodified (oracle/_ref), fresh workspace per QP, "
                                            f"one process per core ({cores})"},
@@ -248,10 +254,9 @@ def main():
                                  "construction; the binding limits of this fp64 warp-per-robot kernel are "
                                  "instruction issue/latency and shared-memory bandwidth (DESIGN.md §7)"}}
     if not args.no_cpu_baseline:
-        sample = min(n_per_gpu, 2048)
-        v, wall = cpu_reference_rate(rec[:sample], rt[:sample], params, h, cores)
+        v, wall, sample = cpu_reference_rate(rec, rt, params, h, cores)
         line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} records of this workload, one pass ({wall:.1f} s wall); QP "
+                                "sample": f"{sample} records drawn cyclically from this workload, one pass ({wall:.1f} s wall); QP "
                                           "builder restatement + the reference's vendored OSQP 0.6.0 compiled "
                                           "unmodified (oracle/_ref), reference settings, fresh workspace per QP, "
                                           f"one process per core"}
