@@ -72,7 +72,7 @@ struct Dims {
   static constexpr int NVS = (NV + NL - 1) / NL;
   static constexpr int NP = (NW + 1) / 2;             // row pairs (i, NW-1-i) of the triangle
   static constexpr int NRS = 2 * ((NP + NL - 1) / NL);  // (unused) triangle rows per lane
-  static constexpr int NTRI = NW * (NW - 1) / 2;      // packed strictly-lower triangle
+  static constexpr int NTRI = NW * (NW + 1) / 2;      // packed lower triangle (row i at i(i+1)/2; slot i of row i unused)
   // shared-memory layout (doubles)
   static constexpr int OFF_WP = 0;                       // [NTRI] Hm -> L -> W = L^-1, row-packed
   static constexpr int OFF_SCR = OFF_WP + NTRI;          // scratch: vecA vecB vt vg vw Finv
@@ -95,11 +95,12 @@ struct Dims {
   static_assert(NLS * 21 <= NTRI && 288 + 72 <= NTRI, "staging does not fit in the triangle buffer");
 };
 
-// Row-packed strictly-lower triangle: element (i, k), k < i, lives at i(i-1)/2 + k.  Triangular
-// numbers are a complete residue system mod 2^m, so 16 consecutive rows at the same column hit
-// 16 different 8-byte banks (row walks are conflict-free) and a fixed row is contiguous in k
-// (column walks across lanes are conflict-free too).
-MPC_LANEFN int tri(int i) { return (i * (i - 1)) >> 1; }
+// Row-packed lower triangle: element (i, k), k < i, lives at i(i+1)/2 + k (row i owns i+1 slots,
+// the last one is unused - the diagonal is kept in dinv[]).  Triangular numbers t_n = n(n+1)/2,
+// n = 16m..16m+15, are a complete residue system mod 16, so the 16 rows of a half-warp hit 16
+// different 8-byte bank pairs at the same column (row walks are conflict-free) and a fixed row
+// is contiguous in k (column walks across lanes touch consecutive words).
+MPC_LANEFN int tri(int i) { return (i * (i + 1)) >> 1; }
 // Rows of an n x n triangle owned by `lane`: rows are paired (p, n-1-p) so that every lane
 // carries the same number of elements (n-1) per pair.
 MPC_LANEFN int rowmap(int lane, int n, int r) {
@@ -861,24 +862,24 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     for (int c = lane; c < NW; c += NL) {
       double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int i = c + 1;
-      const double* p = Wp + tri(i) + c;     // &W[i][c]; W[i+1][c] = p[i]
+      const double* p = Wp + tri(i) + c;     // &W[i][c]; W[i+1][c] = p[i+1]
       if ((i & 1) && i < NW) {               // align i to even so that vw pairs are 16-byte aligned
         a0 += p[0] * vw[i];
-        p += i;
+        p += i + 1;
         ++i;
       }
       for (; i + 3 < NW; i += 4) {
         const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
         const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
         a0 += p[0] * y01.x;
-        a1 += p[i] * y01.y;
-        a2 += p[2 * i + 1] * y23.x;
-        a3 += p[3 * i + 3] * y23.y;
-        p += 4 * i + 6;
+        a1 += p[i + 1] * y01.y;
+        a2 += p[2 * i + 3] * y23.x;
+        a3 += p[3 * i + 6] * y23.y;
+        p += 4 * i + 10;
       }
       for (; i < NW; ++i) {
         a0 += p[0] * vw[i];
-        p += i;
+        p += i + 1;
       }
       vt[c] = (a0 + a1) + (a2 + a3);
     }
