@@ -149,6 +149,77 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
                               float* h_grf_full,
                               int32_t* h_status);
 
+/* ---------------------------------------------------------------------------------------
+ * Locomotion tick fused around the QP (one launch per control tick, one CTA per robot):
+ * leg FK/Jacobian, gait phases + horizon table, CoM height / ground normal, foot placement,
+ * swing Bezier, QP marshalling, [QP solve when the MPC is due], Cartesian PD + J^T f torque
+ * map.  Replaces the per-robot Python loop
+ *   reference/RL_Environment/tasks/aliengo.py:252-256 -> RobotRunnerMin.run (RobotRunnerMin.py:54-76)
+ *   -> ConvexMPCLocomotion.run (ConvexMPCLocomotion.py:222-378) -> LegController.updateCommand.
+ * StateEstimator.update()'s outputs are an input (`d_est`); see DESIGN.md.
+ * ------------------------------------------------------------------------------------- */
+/* robot geometry / default-weight row (float32), reference Quadruped.py:16-73 */
+#define MPC_GEOM_ABAD     0
+#define MPC_GEOM_HIP      1
+#define MPC_GEOM_KNEE     2
+#define MPC_GEOM_LOCX     3   /* _abadLocation */
+#define MPC_GEOM_LOCY     4
+#define MPC_GEOM_LOCZ     5
+#define MPC_GEOM_HEIGHT   6   /* _bodyHeight */
+#define MPC_GEOM_MU       7
+#define MPC_GEOM_WEIGHTS  8   /* 13 default MPC weights */
+#define MPC_GEOM_STRIDE  24
+/* StateEstimator.update() outputs per robot (float32): vBody, omegaBody, rpyBody, ground_R_body_frame (row-major) */
+#define MPC_EST_VBODY      0
+#define MPC_EST_OMEGABODY  3
+#define MPC_EST_RPYBODY    6
+#define MPC_EST_GROUNDR    9
+#define MPC_EST_STRIDE    18
+/* commands per robot (float32): vx, vy, yaw rate, then 13 MPC weights (used when has_weights) */
+#define MPC_CMD_STRIDE    16
+/* persistent per-robot tick state (float32 row; the first six slots hold int32 bit patterns) */
+#define MPC_ST_COUNTER     0   /* int  iterationCounter                         */
+#define MPC_ST_FIRSTRUN    1   /* int                                           */
+#define MPC_ST_FIRSTSWING  2   /* int[4]                                        */
+#define MPC_ST_SWINGREM    6   /* [4]  swingTimeRemaining                       */
+#define MPC_ST_P0         10   /* [4][3] swing start                            */
+#define MPC_ST_PF         22   /* [4][3] swing target                           */
+#define MPC_ST_TRAJP      34   /* [4][3] last swing position                    */
+#define MPC_ST_TRAJV      46   /* [4][3] last swing velocity                    */
+#define MPC_ST_FFF        58   /* [4][3] f_ff of the last MPC solve             */
+#define MPC_ST_POSZ       70   /* estimator CoM height                          */
+#define MPC_ST_CPHASE     71   /* [4]  estimator contact phase                  */
+#define MPC_ST_HIST       75   /* [4][3] foot contact history                   */
+#define MPC_ST_NORMAL     87   /* [3]  ground normal (yaw frame)                */
+#define MPC_TICK_STATE_STRIDE 96
+
+typedef struct MpcB200TickParams {
+  float dt;                /* Parameters.controller_dt (0.01)                       */
+  int   iters_between_mpc; /* int(27/(1000*dt)) = 2 (RobotRunnerMin.py:21-22)        */
+  int   flat_ground;       /* Parameters.flat_ground                                */
+  float bonus_swing;       /* Parameters.cmpc_bonus_swing                           */
+  int   reserved[4];
+} MpcB200TickParams;
+
+/*
+ * One control tick for n_robots robots (device pointers, asynchronous on `stream`).
+ *   d_dof    [n, 12, 2] float32: joint position / velocity interleaved (Isaac dof_state layout)
+ *   d_est    [n, MPC_EST_STRIDE] float32
+ *   d_cmd    [n, MPC_CMD_STRIDE] float32; has_weights != 0 -> weights from d_cmd, else robot default
+ *   d_gait   [n] int32 gait ids (ConvexMPCLocomotion.py:227-241) or NULL (trot)
+ *   d_robot_params [n_types, 12], d_robot_geom [n_types, MPC_GEOM_STRIDE], d_robot_type [n] or NULL
+ *   d_state  [n, MPC_TICK_STATE_STRIDE] float32, read and written
+ *   d_torques [n, 12] float32 out
+ *   d_grf0   [n, 12] float32 out or NULL: written for robots whose MPC fired this tick
+ *   d_records[n, MPC_REC_STRIDE(h)] float32 out or NULL: the QP record built this tick (tests)
+ *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise
+ */
+int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick,
+                  const float* d_dof, const float* d_est, const float* d_cmd, int has_weights,
+                  const int32_t* d_gait, const float* d_robot_params, const float* d_robot_geom,
+                  const int32_t* d_robot_type, int n_robots, float* d_state, float* d_torques,
+                  float* d_grf0, float* d_records, int32_t* d_solved, void* stream);
+
 /* Debug / test hook: run ONE record through the solve kernel and copy back the
  * quantities the kernel never materialises in production: the dense Hessian
  * P[n*n] (row-major, n = 12h) and gradient q[n] of the condensed QP

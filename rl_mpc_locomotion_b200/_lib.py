@@ -16,7 +16,7 @@ MODE_OSQP, MODE_FIXED = 0, 1
 STATUS_SOLVED, STATUS_MAX_ITER = 1, -2
 EXPORTS = ("mpc_b200_default_settings", "mpc_b200_version", "mpc_b200_last_error",
            "mpc_b200_device_count", "mpc_b200_kernel_info", "mpc_b200_solve_batch",
-           "mpc_b200_solve_batch_host", "mpc_b200_debug_build_qp")
+           "mpc_b200_solve_batch_host", "mpc_b200_debug_build_qp", "mpc_b200_tick")
 
 
 class MpcB200Error(RuntimeError):
@@ -31,6 +31,12 @@ class Settings(C.Structure):
                 ("dt", C.c_double), ("alpha", C.c_double), ("rho", C.c_double), ("sigma", C.c_double),
                 ("relax", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double),
                 ("delta", C.c_double), ("rho_tol_ratio", C.c_double), ("reserved_d", C.c_double * 3)]
+
+
+class TickParams(C.Structure):
+    """Mirror of ``MpcB200TickParams``."""
+    _fields_ = [("dt", C.c_float), ("iters_between_mpc", C.c_int), ("flat_ground", C.c_int),
+                ("bonus_swing", C.c_float), ("reserved", C.c_int * 4)]
 
 
 _lib = None
@@ -59,6 +65,9 @@ def lib():
         L.mpc_b200_solve_batch_host.restype = C.c_int
         L.mpc_b200_debug_build_qp.argtypes = [C.POINTER(Settings), vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_debug_build_qp.restype = C.c_int
+        L.mpc_b200_tick.argtypes = [C.POINTER(Settings), C.POINTER(TickParams), vp, vp, vp, C.c_int, vp, vp, vp, vp,
+                                    C.c_int, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_tick.restype = C.c_int
         _lib = L
     return _lib
 

@@ -16,6 +16,7 @@
 
 #include "../../include/mpc_b200.h"
 #include "mpc_warp_solver.cuh"
+#include "mpc_tick.cuh"
 
 namespace {
 
@@ -113,6 +114,90 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                       status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
                       info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr,
                       dbg ? dbg + (size_t)robot * dbg_stride : nullptr, lane);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Fused Locomotion tick: tick_pre -> [solve_robot] -> tick_post, one CTA per robot.
+// ---------------------------------------------------------------------------------------
+template <int H>
+struct TickCfg {
+  using K = KernelCfg<H>;
+  static constexpr int OFF_STATE = K::SMEM_BYTES;                    // float[96]
+  static constexpr int OFF_LEGS = OFF_STATE + MPC_TICK_STATE_STRIDE * 4;  // float[4][32]
+  static constexpr int OFF_IN = OFF_LEGS + 4 * mpc::LG_STRIDE * 4;   // dof[24] est[18] cmd[16] geom[24] grf[12]
+  static constexpr int SMEM_BYTES = OFF_IN + (24 + 18 + 16 + 24 + 12 + 2) * 4;
+};
+
+template <int H>
+__global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
+mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const float* __restrict__ dof,
+                const float* __restrict__ est, const float* __restrict__ cmd, int has_weights,
+                const int32_t* __restrict__ gait, const float* __restrict__ robot_params,
+                const float* __restrict__ robot_geom, const int32_t* __restrict__ robot_type, int n_robots,
+                float* __restrict__ state, float* __restrict__ torques, float* __restrict__ grf0,
+                float* __restrict__ records, int32_t* __restrict__ solved) {
+  using K = KernelCfg<H>;
+  using T = TickCfg<H>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  float* rec_s = reinterpret_cast<float*>(smem_raw + K::OFF_REC);
+  float* rp_s = reinterpret_cast<float*>(smem_raw + K::OFF_RP);
+  float* st_s = reinterpret_cast<float*>(smem_raw + T::OFF_STATE);
+  float* legs_s = reinterpret_cast<float*>(smem_raw + T::OFF_LEGS);
+  float* dof_s = reinterpret_cast<float*>(smem_raw + T::OFF_IN);
+  float* est_s = dof_s + 24;
+  float* cmd_s = est_s + 18;
+  float* geom_s = cmd_s + 16;
+  float* grf_s = geom_s + 24;
+  int32_t* stat_s = reinterpret_cast<int32_t*>(grf_s + 12);
+  const int lane = threadIdx.x;
+  const int robot = blockIdx.x;
+  if (robot >= n_robots) return;
+  const int type = robot_type ? robot_type[robot] : 0;
+  for (int i = lane; i < MPC_TICK_STATE_STRIDE; i += MPC_NL) st_s[i] = state[(size_t)robot * MPC_TICK_STATE_STRIDE + i];
+  if (lane < 24) {
+    dof_s[lane] = dof[(size_t)robot * 24 + lane];
+    geom_s[lane] = robot_geom[(size_t)type * MPC_GEOM_STRIDE + lane];
+  }
+  if (lane < 18) est_s[lane] = est[(size_t)robot * MPC_EST_STRIDE + lane];
+  if (lane < 16) cmd_s[lane] = cmd[(size_t)robot * MPC_CMD_STRIDE + lane];
+  if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
+  if (lane == 0) stat_s[0] = 0;
+  for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) rec_s[i] = 0.0f;
+  __syncthreads();
+  const int g = gait ? gait[robot] : 0;
+  const int do_solve = mpc::tick_pre<H>(dof_s, est_s, cmd_s, has_weights, g, geom_s, tp, st_s, rec_s, legs_s, lane);
+  if (records)
+    for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) records[(size_t)robot * K::REC_FLOATS + i] = rec_s[i];
+  if (do_solve) {
+    mpc::fill_tables<H>(sm, prm.dt, lane);
+    mpc::solve_robot<H>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, nullptr, nullptr, lane);
+    __syncthreads();
+    if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
+  }
+  mpc::tick_post(est_s, geom_s, do_solve ? grf_s : nullptr, st_s, legs_s, torques + (size_t)robot * 12, lane);
+  for (int i = lane; i < MPC_TICK_STATE_STRIDE; i += MPC_NL) state[(size_t)robot * MPC_TICK_STATE_STRIDE + i] = st_s[i];
+  if (solved && lane == 0) solved[robot] = stat_s[0];
+}
+
+template <int H>
+int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* est,
+                const float* cmd, int has_weights, const int32_t* gait, const float* rp, const float* geom,
+                const int32_t* rt, int n, float* state, float* torques, float* grf0, float* records,
+                int32_t* solved, cudaStream_t stream) {
+  using T = TickCfg<H>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(mpc_tick_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem, tick)");
+  if (n <= 0) return MPC_B200_OK;
+  mpc_tick_kernel<H><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, est, cmd, has_weights, gait, rp, geom, rt, n,
+                                                         state, torques, grf0, records, solved);
+  CK(cudaGetLastError());
+  return MPC_B200_OK;
 }
 
 mpc::SolveParams to_params(const MpcB200Settings& s) {
@@ -328,6 +413,44 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_re
   if (h_status) CK(cudaMemcpyAsync(h_status, d_st, (size_t)n_robots * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MPC_B200_OK;
+}
+
+int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick, const float* d_dof,
+                  const float* d_est, const float* d_cmd, int has_weights, const int32_t* d_gait,
+                  const float* d_robot_params, const float* d_robot_geom, const int32_t* d_robot_type,
+                  int n_robots, float* d_state, float* d_torques, float* d_grf0, float* d_records,
+                  int32_t* d_solved, void* stream) {
+  int rc = check_settings(settings);
+  if (rc) return rc;
+  if (!tick || tick->iters_between_mpc <= 0 || !(tick->dt > 0)) {
+    snprintf(g_err, sizeof(g_err), "invalid tick parameters");
+    return MPC_B200_EINVAL;
+  }
+  if (n_robots < 0 || (n_robots > 0 && (!d_dof || !d_est || !d_cmd || !d_robot_params || !d_robot_geom ||
+                                        !d_state || !d_torques))) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+    return MPC_B200_EINVAL;
+  }
+  if (mpc_b200_device_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
+    return MPC_B200_ENOGPU;
+  }
+  if (n_robots == 0) return MPC_B200_OK;
+  mpc::SolveParams prm = to_params(*settings);
+  // the MPC timestep is dt * iterationsBetweenMPC (ConvexMPCLocomotion.py:58)
+  prm.dt = (double)tick->dt * tick->iters_between_mpc;
+  mpc::TickParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.dt = tick->dt;
+  tp.iters_between_mpc = tick->iters_between_mpc;
+  tp.flat_ground = tick->flat_ground;
+  tp.bonus_swing = tick->bonus_swing;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (settings->horizon == 10)
+    return launch_tick<10>(prm, tp, d_dof, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
+                           d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, st);
+  return launch_tick<16>(prm, tp, d_dof, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
+                         d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, st);
 }
 
 int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_record,

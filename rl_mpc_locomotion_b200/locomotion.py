@@ -1,0 +1,71 @@
+"""Batched, device-resident Locomotion tick (the new entry point for the RL environment).
+
+Replaces the host loop ``for idx, controller in enumerate(self.controllers): controller.run(...)``
+(reference/RL_Environment/tasks/aliengo.py:252-256) — i.e. ``RobotRunnerMin.run``
+(robot_runner/RobotRunnerMin.py:54-76) minus ``StateEstimator.update`` — by ONE kernel launch
+per control tick: leg FK/Jacobian, gait phases and horizon table, CoM height / ground normal,
+foot placement, swing Bezier, QP marshalling, the OSQP-faithful QP solve when the MPC is due,
+and the Cartesian-PD + J^T f torque map.  All per-robot controller state
+(iterationCounter, firstSwing, swing trajectories, f_ff, estimator height / contact phase /
+contact history / ground normal) lives in one ``[N, 96]`` device tensor (``state``) so it can be
+checkpointed with ``torch.save`` and reset per robot by overwriting rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .robots import TICK_STATE_STRIDE, geom_table, initial_tick_state, params_table
+
+
+class BatchedLocomotion:
+    def __init__(self, robot_type, gait, horizon: int = 10, device="cuda", dt: float = 0.01,
+                 iters_between_mpc: int = 2, flat_ground: bool = False, **settings):
+        """``robot_type`` / ``gait``: per-robot int arrays (RobotType values; gait ids as in
+        ConvexMPCLocomotion.run :227-241 — the reference can only express ONE global gait,
+        Parameters.cmpc_gait)."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MpcB200Error("BatchedLocomotion needs a CUDA device: there is no CPU path")
+        self.settings = _lib.default_settings(horizon=horizon, **settings)
+        self.tick_params = _lib.TickParams(dt, iters_between_mpc, int(flat_ground), 0.0)
+        rt = np.atleast_1d(np.asarray(robot_type, dtype=np.int32))
+        self.n = len(rt)
+        dev = self.device
+        self.robot_type = torch.from_numpy(rt).to(dev)
+        self.gait = torch.from_numpy(np.broadcast_to(np.asarray(gait, dtype=np.int32), rt.shape).copy()).to(dev)
+        self.robot_params = torch.from_numpy(params_table()).to(dev)
+        self.robot_geom = torch.from_numpy(geom_table()).to(dev)
+        self._fresh = torch.from_numpy(initial_tick_state(rt)).to(dev)
+        self.state = self._fresh.clone()
+        self.torques = torch.empty((self.n, 12), dtype=torch.float32, device=dev)
+        self.grf0 = torch.zeros((self.n, 12), dtype=torch.float32, device=dev)
+        self.solved = torch.zeros((self.n,), dtype=torch.int32, device=dev)
+
+    def reset(self, idx=None):
+        """``controller.reset()`` for the given robots (aliengo.py:333-334); all when None."""
+        if idx is None:
+            self.state.copy_(self._fresh)
+        else:
+            self.state[idx] = self._fresh[idx]
+
+    def run(self, dof_state: torch.Tensor, est: torch.Tensor, commands: torch.Tensor, has_weights: bool = True,
+            records_out: torch.Tensor | None = None) -> torch.Tensor:
+        """One control tick.  ``dof_state`` [N,12,2] (pos, vel), ``est`` [N,18] (vBody, omegaBody,
+        rpyBody, ground_R_body row-major — StateEstimator.update outputs), ``commands`` [N,16]
+        (vx, vy, yaw rate, 13 weights).  Returns ``torques`` [N,12] (float32, device)."""
+        for t, shape in ((dof_state, (self.n, 12, 2)), (est, (self.n, 18)), (commands, (self.n, 16))):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mpc_b200_tick(C.byref(self.settings), C.byref(self.tick_params), p(dof_state), p(est),
+                                          p(commands), int(has_weights), p(self.gait), p(self.robot_params),
+                                          p(self.robot_geom), p(self.robot_type), self.n, p(self.state),
+                                          p(self.torques), p(self.grf0), p(records_out), p(self.solved),
+                                          C.c_void_p(stream))
+        _lib.check(rc, "mpc_b200_tick")
+        return self.torques

@@ -69,6 +69,36 @@ ROBOTS = {
 }
 
 SIDE_SIGN = (1.0, -1.0, 1.0, -1.0)   # reference utils.py:7
+GEOM_STRIDE = 24        # MPC_GEOM_STRIDE (include/mpc_b200.h)
+TICK_STATE_STRIDE = 96  # MPC_TICK_STATE_STRIDE
+
+
+def geom_row(m: RobotModel) -> np.ndarray:
+    """Geometry / default-weight row of the device tick (MPC_GEOM_* layout)."""
+    row = np.zeros(GEOM_STRIDE, dtype=np.float32)
+    row[0:3] = (m.abad_link, m.hip_link, m.knee_link)
+    row[3:6] = m.abad_location
+    row[6], row[7] = m.body_height, m.friction
+    row[8:21] = m.mpc_weights
+    return row
+
+
+def geom_table() -> np.ndarray:
+    return np.stack([geom_row(ROBOTS[t]) for t in RobotType])
+
+
+def initial_tick_state(robot_type) -> np.ndarray:
+    """Fresh per-robot tick state (MPC_ST_* layout) = a just-initialised ConvexMPCLocomotion +
+    StateEstimator (ConvexMPCLocomotion.py:89-114, StateEstimator.py:27-48): counter 0,
+    firstRun, firstSwing x4, estimator height = nominal body height, ground normal = +z."""
+    rt = np.atleast_1d(np.asarray(robot_type, dtype=np.int64))
+    st = np.zeros((len(rt), TICK_STATE_STRIDE), dtype=np.float32)
+    sti = st.view(np.int32)
+    sti[:, 1] = 1
+    sti[:, 2:6] = 1
+    st[:, 70] = [ROBOTS[RobotType(int(t))].body_height for t in rt]
+    st[:, 89] = 1.0
+    return st
 
 
 def params_table() -> np.ndarray:

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "warp_emu", "emu_main.cc")
 _SO = os.path.join(_HERE, "warp_emu", "libmpc_emu.so")
 _HDRS = [os.path.join(_HERE, "..", "rl_mpc_locomotion_b200", "csrc", f)
-         for f in ("mpc_warp_solver.cuh", "warp_prog.h")] + [os.path.join(_HERE, "..", "include", "mpc_b200.h")]
+         for f in ("mpc_warp_solver.cuh", "warp_prog.h", "mpc_tick.cuh")] + [os.path.join(_HERE, "..", "include", "mpc_b200.h")]
 
 
 class SolveParams(C.Structure):
@@ -78,3 +78,32 @@ def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg
         out["E"] = dbg[:, nv + nv * nv + nv: nv + nv * nv + nv + 20 * horizon]
         out["c"] = dbg[:, -1]
     return out
+
+
+class TickParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("iters_between_mpc", C.c_int), ("flat_ground", C.c_int),
+                ("bonus_swing", C.c_float), ("reserved", C.c_int * 4)]
+
+
+def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robot_type, flat_ground=False,
+         params=None, dt=0.01, iters_between_mpc=2):
+    """One emulated control tick; `state` [N,96] float32 is updated in place."""
+    n = state.shape[0]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    dof, est, cmd, rp, geom = f32(dof), f32(est), f32(cmd), f32(robot_params), f32(robot_geom)
+    gait = np.ascontiguousarray(gait, dtype=np.int32)
+    rt = np.ascontiguousarray(robot_type, dtype=np.int32)
+    assert state.dtype == np.float32 and state.flags.c_contiguous
+    tp = TickParams(dt, iters_between_mpc, int(flat_ground), 0.0)
+    prm = params or default_params()
+    torques = np.zeros((n, 12), np.float32)
+    grf0 = np.zeros((n, 12), np.float32)
+    records = np.zeros((n, 96), np.float32)
+    solved = np.zeros(n, np.int32)
+    P = C.c_void_p
+    rc = lib().mpc_emu_tick(C.byref(prm), C.byref(tp), P(dof.ctypes.data), P(est.ctypes.data), P(cmd.ctypes.data),
+                            int(has_weights), P(gait.ctypes.data), P(rp.ctypes.data), P(geom.ctypes.data),
+                            P(rt.ctypes.data), n, P(state.ctypes.data), P(torques.ctypes.data), P(grf0.ctypes.data),
+                            P(records.ctypes.data), P(solved.ctypes.data))
+    assert rc == 0
+    return dict(torques=torques, grf0=grf0, records=records, solved=solved)

@@ -1,0 +1,114 @@
+"""Golden Locomotion-tick fixtures from the UNMODIFIED reference Python.
+
+Drives the reference's own objects (RobotRunnerMin wiring, reference/MPC_Controller/
+robot_runner/RobotRunnerMin.py:54-76) on a simulator-free kinematic replay, with the oracle's
+`mpc_osqp` pybind module (oracle/mpc_osqp*.so: reference OSQP, COLD mode = fresh workspace
+per solve) standing in for the native module that cannot be built here.  Logs, per tick, the
+inputs, the StateEstimator.update() outputs, the 13 QP arguments when the MPC fires, and the
+resulting leg torques.  Run in the build container only (needs /root/reference).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+os.environ["MPC_ORACLE_MODE"] = "cold"
+sys.path.insert(0, os.path.join(ROOT, "oracle"))   # provides `import mpc_osqp`
+sys.path.insert(0, "/root/reference")
+
+import contextlib, io  # noqa: E402
+with contextlib.redirect_stdout(io.StringIO()):
+    from MPC_Controller.Parameters import Parameters
+    from MPC_Controller.common.Quadruped import RobotType
+    from MPC_Controller.robot_runner.RobotRunnerMin import RobotRunnerMin
+    from MPC_Controller.utils import GaitType
+
+Parameters.bridge_MPC_to_RL = True     # array inputs, as the RL env uses (aliengo.py:247-256)
+
+
+def quat_xyzw(roll, pitch, yaw):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    w = cr * cp * cy + sr * sp * sy
+    x = sr * cp * cy - cr * sp * sy
+    y = cr * sp * cy + sr * cp * sy
+    z = cr * cp * sy - sr * sp * cy
+    return np.array([x, y, z, w])
+
+
+def run_case(name, robot, gait, flat, ticks, seed, with_weights):
+    rng = np.random.default_rng(seed)
+    Parameters.cmpc_gait = gait
+    Parameters.flat_ground = flat
+    with contextlib.redirect_stdout(io.StringIO()):
+        runner = RobotRunnerMin()
+        runner.init(robot)
+    log = {k: [] for k in ("dof", "body", "cmd", "vBody", "omegaBody", "rpyBody", "groundR", "z_pre", "z_post",
+                           "normal", "contact_phase", "torques", "f_ff", "counter", "solved", "qp_args", "qp_out")}
+    calls = []
+    real = runner.cMPC._cpp_mpc.compute_contact_forces
+
+    class Proxy:
+        def compute_contact_forces(self, *a):
+            out = real(*a)
+            calls.append(([np.asarray(x, dtype=np.float64).reshape(-1) for x in a], np.asarray(out, dtype=np.float64)))
+            return out
+
+        def reset_solver(self):
+            pass
+    runner.cMPC._cpp_mpc = Proxy()
+    stand = np.tile([0.0, 0.8, -1.6], 4)
+    ph = rng.uniform(0, 6.28, 12)
+    w0 = rng.uniform(3.0, 9.0, 12)
+    for t in range(ticks):
+        tt = 0.01 * t
+        q = stand + 0.12 * np.sin(w0 * tt + ph)
+        qd = 0.12 * w0 * np.cos(w0 * tt + ph)
+        dof = np.stack([q, qd], 1).astype(np.float32)
+        rpy = np.array([0.06 * np.sin(3.1 * tt + 0.3), 0.05 * np.sin(2.3 * tt + 1.1), 0.2 * np.sin(0.9 * tt)])
+        body = np.concatenate([[0.0, 0.0, 0.35], quat_xyzw(*rpy), [0.5 + 0.1 * np.sin(2 * tt), 0.05 * np.cos(3 * tt), 0.02 * np.sin(5 * tt)],
+                               [0.2 * np.sin(4 * tt), 0.15 * np.cos(3.3 * tt), 0.3 * np.sin(1.7 * tt)]]).astype(np.float32)
+        cmd = [0.5, 0.05, 0.3]
+        if with_weights:
+            cmd = cmd + list(rng.uniform(-1, 1, 12) * np.array(Parameters.MPC_param_scale) + np.array(Parameters.MPC_param_const)) + [0.0]
+        cmd = np.asarray(cmd, dtype=np.float32)
+        # --- RobotRunnerMin.run, step by step on the reference's own objects
+        runner._desiredStateCommand.updateCommand(cmd)
+        runner._legController.updateData(dof)
+        runner._legController.zeroCommand()
+        runner._stateEstimator.update(body)
+        se = runner._stateEstimator.getResult()
+        log["vBody"].append(np.asarray(se.vBody, np.float64).reshape(3))
+        log["omegaBody"].append(np.asarray(se.omegaBody, np.float64).reshape(3))
+        log["rpyBody"].append(np.asarray(se.rpyBody, np.float64).reshape(3))
+        log["groundR"].append(np.asarray(runner._stateEstimator.ground_R_body_frame, np.float64).reshape(9))
+        log["z_pre"].append(float(se.position[2]))
+        n_before = len(calls)
+        runner.cMPC.run(runner.data)
+        tau = runner._legController.updateCommand()
+        log["dof"].append(dof); log["body"].append(body)
+        log["cmd"].append(np.concatenate([cmd, np.zeros(16 - len(cmd), np.float32)]))
+        log["z_post"].append(float(se.position[2]))
+        log["normal"].append(np.asarray(se.ground_normal_yaw, np.float64).reshape(3))
+        log["contact_phase"].append(np.asarray(runner._stateEstimator._contactPhase, np.float64).reshape(4))
+        log["torques"].append(np.asarray(tau, np.float64))
+        log["f_ff"].append(np.asarray(runner.cMPC.f_ff, np.float64).reshape(12))
+        log["counter"].append(runner.cMPC.iterationCounter)
+        solved = len(calls) > n_before
+        log["solved"].append(solved)
+        if solved:
+            a, o = calls[-1]
+            log["qp_args"].append(np.concatenate(a)); log["qp_out"].append(o)
+        else:
+            log["qp_args"].append(np.zeros(96)); log["qp_out"].append(np.zeros(120))
+    out = {k: np.asarray(v) for k, v in log.items()}
+    out["meta"] = np.array([int(robot.value), int(gait.value), int(flat), int(with_weights)])
+    np.savez_compressed(os.path.join(HERE, f"tick_golden_{name}.npz"), **out)
+    print(name, "ticks", ticks, "qp solves", int(out["solved"].sum()), "max |tau|", np.abs(out["torques"]).max())
+
+
+if __name__ == "__main__":
+    run_case("aliengo_trot", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True)
+    run_case("aliengo_walk_flat", RobotType.ALIENGO, GaitType.WALK, True, 60, 2, False)
+    run_case("a1_bound", RobotType.A1, GaitType.BOUND, False, 60, 3, True)

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../rl_mpc_locomotion_b200/csrc/mpc_warp_solver.cuh"
+#include "../../rl_mpc_locomotion_b200/csrc/mpc_tick.cuh"
 
 template <int H>
 static void run(const float* rec, int n, const float* rp, const int* rt, const mpc::SolveParams& prm,
@@ -33,5 +34,42 @@ extern "C" int mpc_emu_solve(const float* rec, int n, int horizon, const float* 
   if (horizon == 10) run<10>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, dbg);
   else if (horizon == 16) run<16>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, dbg);
   else return -1;
+  return 0;
+}
+
+// One emulated control tick for n robots (same sequence as mpc_tick_kernel in mpc_b200.cu).
+extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParams* tp, const float* dof,
+                            const float* est, const float* cmd, int has_weights, const int* gait,
+                            const float* rp, const float* geom, const int* rt, int n, float* state,
+                            float* torques, float* grf0, float* records, int32_t* solved) {
+  constexpr int H = 10;
+  using D = mpc::Dims<H>;
+  mpc::SolveParams prm = *prm_in;
+  prm.dt = (double)tp->dt * tp->iters_between_mpc;
+  std::vector<double> sm(D::SMEM_DOUBLES, 0.0);
+  const int stride = MPC_REC_STRIDE(H);
+  for (int r = 0; r < n; ++r) {
+    const int type = rt ? rt[r] : 0;
+    float rec[stride];
+    std::memset(rec, 0, sizeof(rec));
+    float legs[4 * mpc::LG_STRIDE];
+    std::memset(legs, 0, sizeof(legs));
+    float grf[12] = {0};
+    int32_t st_code = 0;
+    float* st = state + (size_t)r * MPC_TICK_STATE_STRIDE;
+    const float* g = geom + (size_t)type * MPC_GEOM_STRIDE;
+    const float* e = est + (size_t)r * MPC_EST_STRIDE;
+    const int do_solve = mpc::tick_pre<H>(dof + (size_t)r * 24, e, cmd + (size_t)r * MPC_CMD_STRIDE, has_weights,
+                                          gait ? gait[r] : 0, g, *tp, st, rec, legs);
+    if (records) std::memcpy(records + (size_t)r * stride, rec, sizeof(rec));
+    if (do_solve) {
+      mpc::fill_tables<H>(sm.data(), prm.dt);
+      mpc::solve_robot<H>(rec, rp + (size_t)type * MPC_ROBOT_PARAMS_STRIDE, prm, sm.data(), grf, nullptr, &st_code,
+                          nullptr, nullptr, nullptr);
+      if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
+    }
+    mpc::tick_post(e, g, do_solve ? grf : nullptr, st, legs, torques + (size_t)r * 12);
+    if (solved) solved[r] = st_code;
+  }
   return 0;
 }
