@@ -156,7 +156,8 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
  * map.  Replaces the per-robot Python loop
  *   reference/RL_Environment/tasks/aliengo.py:252-256 -> RobotRunnerMin.run (RobotRunnerMin.py:54-76)
  *   -> ConvexMPCLocomotion.run (ConvexMPCLocomotion.py:222-378) -> LegController.updateCommand.
- * StateEstimator.update()'s outputs are an input (`d_est`); see DESIGN.md.
+ * StateEstimator.update() (StateEstimator.py:57-97, float16 rotations reproduced bit for bit)
+ * runs in the same launch when `d_body` (Isaac root_states rows) is given instead of `d_est`.
  * ------------------------------------------------------------------------------------- */
 /* robot geometry / default-weight row (float32), reference Quadruped.py:16-73 */
 #define MPC_GEOM_ABAD     0
@@ -204,7 +205,10 @@ typedef struct MpcB200TickParams {
 /*
  * One control tick for n_robots robots (device pointers, asynchronous on `stream`).
  *   d_dof    [n, 12, 2] float32: joint position / velocity interleaved (Isaac dof_state layout)
- *   d_est    [n, MPC_EST_STRIDE] float32
+ *   d_body   [n, 13] float32 root states (pos3, quat xyzw, lin vel3, ang vel3; aliengo.py:248)
+ *            or NULL; when given, StateEstimator.update runs on the device
+ *   d_est    [n, MPC_EST_STRIDE] float32 or NULL: precomputed StateEstimator.update outputs
+ *            (exactly one of d_body / d_est must be non-NULL)
  *   d_cmd    [n, MPC_CMD_STRIDE] float32; has_weights != 0 -> weights from d_cmd, else robot default
  *   d_gait   [n] int32 gait ids (ConvexMPCLocomotion.py:227-241) or NULL (trot)
  *   d_robot_params [n_types, 12], d_robot_geom [n_types, MPC_GEOM_STRIDE], d_robot_type [n] or NULL
@@ -215,7 +219,8 @@ typedef struct MpcB200TickParams {
  *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise
  */
 int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick,
-                  const float* d_dof, const float* d_est, const float* d_cmd, int has_weights,
+                  const float* d_dof, const float* d_body, const float* d_est, const float* d_cmd,
+                  int has_weights,
                   const int32_t* d_gait, const float* d_robot_params, const float* d_robot_geom,
                   const int32_t* d_robot_type, int n_robots, float* d_state, float* d_torques,
                   float* d_grf0, float* d_records, int32_t* d_solved, void* stream);

@@ -132,7 +132,8 @@ struct TickCfg {
 template <int H>
 __global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
 mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const float* __restrict__ dof,
-                const float* __restrict__ est, const float* __restrict__ cmd, int has_weights,
+                const float* __restrict__ body, const float* __restrict__ est, const float* __restrict__ cmd,
+                int has_weights,
                 const int32_t* __restrict__ gait, const float* __restrict__ robot_params,
                 const float* __restrict__ robot_geom, const int32_t* __restrict__ robot_type, int n_robots,
                 float* __restrict__ state, float* __restrict__ torques, float* __restrict__ grf0,
@@ -160,12 +161,16 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     dof_s[lane] = dof[(size_t)robot * 24 + lane];
     geom_s[lane] = robot_geom[(size_t)type * MPC_GEOM_STRIDE + lane];
   }
-  if (lane < 18) est_s[lane] = est[(size_t)robot * MPC_EST_STRIDE + lane];
+  if (est && lane < 18) est_s[lane] = est[(size_t)robot * MPC_EST_STRIDE + lane];
   if (lane < 16) cmd_s[lane] = cmd[(size_t)robot * MPC_CMD_STRIDE + lane];
   if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
   if (lane == 0) stat_s[0] = 0;
   for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) rec_s[i] = 0.0f;
   __syncthreads();
+  if (!est) {  // StateEstimator.update on the device (uses the previous tick's ground normal)
+    if (lane == 0) mpc::estimator_update(body + (size_t)robot * 13, st_s + MPC_ST_NORMAL, est_s);
+    __syncthreads();
+  }
   const int g = gait ? gait[robot] : 0;
   const int do_solve = mpc::tick_pre<H>(dof_s, est_s, cmd_s, has_weights, g, geom_s, tp, st_s, rec_s, legs_s, lane);
   if (records)
@@ -182,8 +187,8 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
 }
 
 template <int H>
-int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* est,
-                const float* cmd, int has_weights, const int32_t* gait, const float* rp, const float* geom,
+int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* body,
+                const float* est, const float* cmd, int has_weights, const int32_t* gait, const float* rp, const float* geom,
                 const int32_t* rt, int n, float* state, float* torques, float* grf0, float* records,
                 int32_t* solved, cudaStream_t stream) {
   using T = TickCfg<H>;
@@ -194,7 +199,7 @@ int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const fl
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem, tick)");
   if (n <= 0) return MPC_B200_OK;
-  mpc_tick_kernel<H><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, est, cmd, has_weights, gait, rp, geom, rt, n,
+  mpc_tick_kernel<H><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp, geom, rt, n,
                                                          state, torques, grf0, records, solved);
   CK(cudaGetLastError());
   return MPC_B200_OK;
@@ -416,7 +421,8 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_re
 }
 
 int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick, const float* d_dof,
-                  const float* d_est, const float* d_cmd, int has_weights, const int32_t* d_gait,
+                  const float* d_body, const float* d_est, const float* d_cmd, int has_weights,
+                  const int32_t* d_gait,
                   const float* d_robot_params, const float* d_robot_geom, const int32_t* d_robot_type,
                   int n_robots, float* d_state, float* d_torques, float* d_grf0, float* d_records,
                   int32_t* d_solved, void* stream) {
@@ -426,8 +432,8 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
     snprintf(g_err, sizeof(g_err), "invalid tick parameters");
     return MPC_B200_EINVAL;
   }
-  if (n_robots < 0 || (n_robots > 0 && (!d_dof || !d_est || !d_cmd || !d_robot_params || !d_robot_geom ||
-                                        !d_state || !d_torques))) {
+  if (n_robots < 0 || (n_robots > 0 && (!d_dof || (!d_est == !d_body) || !d_cmd || !d_robot_params ||
+                                        !d_robot_geom || !d_state || !d_torques))) {
     snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
     return MPC_B200_EINVAL;
   }
@@ -447,9 +453,9 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
   tp.bonus_swing = tick->bonus_swing;
   cudaStream_t st = (cudaStream_t)stream;
   if (settings->horizon == 10)
-    return launch_tick<10>(prm, tp, d_dof, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
+    return launch_tick<10>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
                            d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, st);
-  return launch_tick<16>(prm, tp, d_dof, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
+  return launch_tick<16>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
                          d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, st);
 }
 

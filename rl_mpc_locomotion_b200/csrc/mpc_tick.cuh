@@ -12,9 +12,9 @@
 // tick_pre() builds the QP's problem record straight into shared memory (it never touches
 // HBM), the caller runs solve_robot() when the MPC is due (every iterationsBetweenMPC ticks,
 // ConvexMPCLocomotion.py:217-220), tick_post() turns forces + swing trajectories into joint
-// torques.  The StateEstimator.update() part (quaternion -> fp16 rotation, body-frame
-// velocities, rpyBody; StateEstimator.py:57-97) is an INPUT of this kernel (`est`): it is the
-// next row to move on device.
+// torques.  StateEstimator.update() (quaternion -> fp16 rotation, body-frame velocities,
+// rpyBody; StateEstimator.py:57-97) is estimator_update() below and runs in the same launch
+// when the caller passes raw root states instead of precomputed estimator outputs.
 //
 // Arithmetic follows the reference's dtypes: float32 arrays, double where the reference mixes
 // in Python floats, and fp16-rounded sin/cos in the yaw-correction rotation
@@ -81,6 +81,88 @@ MPC_LANEFN void gait_leg(int gait, int leg, float* off, float* dur) {
 
 MPC_LANEFN float bez(float x) { return x * x * x + 3.0f * (x * x * (1.0f - x)); }   // interplation.py:4-11
 MPC_LANEFN float dbez(float x) { return 6.0f * x * (1.0f - x); }                     // interplation.py:13-20
+
+// ---------------------------------------------------------------------------------------
+// StateEstimator.update (reference/MPC_Controller/common/StateEstimator.py:57-97) with the
+// reference's mixed float16 / float32 arithmetic reproduced operation by operation
+// (math_utils/orientation_tools.py: DTYPE = np.float16; NumPy 2 promotion rules: a Python
+// float next to a float16 scalar is rounded to float16, float16 mat-muls and reductions
+// accumulate in float32 and round once).  body = [pos3, quat xyzw, v_world3, omega_world3],
+// normal = ground_normal_yaw of the previous tick; est = MPC_EST_* outputs.
+// ---------------------------------------------------------------------------------------
+MPC_LANEFN float h16(float v) { return round_f16((double)v); }
+MPC_LANEFN void mm3_f16(const float* a, const float* b, float* o) {   // o = h16(a @ b), row-major
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) o[3 * r + c] = h16(a[3 * r] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c]);
+}
+// quat_to_rpy on a quaternion whose w is a Python float and x, y, z are float16 scalars
+// (what rot_to_quat returns for tr > 0, orientation_tools.py:120-133, 162-175)
+MPC_LANEFN void estimator_update(const float* body, const float* normal, float* est) {
+  const float qx = body[3], qy = body[4], qz = body[5], qw = body[6];
+  // quat_to_rot (orientation_tools.py:135-151): float32 expressions, stored as float16, transposed
+  const float e0 = qw, e1 = qx, e2 = qy, e3 = qz;
+  float Rt[9];  // R before the transpose
+  Rt[0] = 1 - 2 * (e2 * e2 + e3 * e3); Rt[1] = 2 * (e1 * e2 - e0 * e3); Rt[2] = 2 * (e1 * e3 + e0 * e2);
+  Rt[3] = 2 * (e1 * e2 + e0 * e3); Rt[4] = 1 - 2 * (e1 * e1 + e3 * e3); Rt[5] = 2 * (e2 * e3 - e0 * e1);
+  Rt[6] = 2 * (e1 * e3 - e0 * e2); Rt[7] = 2 * (e2 * e3 + e0 * e1); Rt[8] = 1 - 2 * (e1 * e1 + e2 * e2);
+  float rB[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) rB[3 * r + c] = h16(Rt[3 * c + r]);
+  for (int r = 0; r < 3; ++r) {   // vBody = rBody @ vWorld, omegaBody = rBody @ omegaWorld (float32)
+    est[MPC_EST_VBODY + r] = rB[3 * r] * body[7] + rB[3 * r + 1] * body[8] + rB[3 * r + 2] * body[9];
+    est[MPC_EST_OMEGABODY + r] = rB[3 * r] * body[10] + rB[3 * r + 1] * body[11] + rB[3 * r + 2] * body[12];
+  }
+  // yaw of quat_to_rpy(orientation) (float32 args, float16 store)
+  const float yaw16 = h16(atan2f(2.0f * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz));
+  // world_R_yaw = coordinateRotation(Z, yaw) (X(0) and Y(0) are exact identities); we need its transpose
+  const float cz = h16((float)cos((double)yaw16)), sz = h16((float)sin((double)yaw16));
+  const float WyT[9] = {cz, -sz, 0.0f, sz, cz, 0.0f, 0.0f, 0.0f, 1.0f};
+  // yaw_R_ground = get_rot_from_normals([0,0,1], normal) (orientation_tools.py:89-108, incl. the
+  // k1*k1 entry and the un-normalised axis); we need its transpose = R_axis_angle
+  const float k0 = -normal[1], k1 = normal[0], k2 = 0.0f;
+  const float theta = acosf(normal[2]);
+  const float ct = (float)cos((double)theta), st_ = (float)sin((double)theta), vt = (float)(1.0 - cos((double)theta));
+  float Ra[9];
+  Ra[0] = h16(k0 * k0 * vt + ct); Ra[1] = h16(k0 * k1 * vt - k2 * st_); Ra[2] = h16(k0 * k2 * vt + k1 * st_);
+  Ra[3] = h16(k0 * k1 * vt + k2 * st_); Ra[4] = h16(k1 * k1 * vt + ct); Ra[5] = h16(k1 * k2 * vt - k0 * st_);
+  Ra[6] = h16(k0 * k2 * vt - k1 * st_); Ra[7] = h16(k1 * k2 * vt + k0 * st_); Ra[8] = h16(k1 * k1 * vt + ct);
+  // ground_R_body_frame = (rBody @ world_R_yaw.T) @ yaw_R_ground.T ; yaw_R_ground = Ra.T so its .T is Ra
+  float M1[9], G[9];
+  mm3_f16(rB, WyT, M1);
+  mm3_f16(M1, Ra, G);
+  for (int e = 0; e < 9; ++e) est[MPC_EST_GROUNDR + e] = G[e];
+  // rpyBody = quat_to_rpy(rot_to_quat(G)) (orientation_tools.py:162-203); r = G.T
+  const float tr = h16(G[0] + G[4] + G[8]);
+  float w_, x_, y_, z_;   // w_ is a Python float (double in the reference) on the tr > 0 branch
+  double wd;
+  if (tr > 0.0f) {
+    const double S = sqrt((double)h16(tr + 1.0f)) * 2.0;
+    wd = 0.25 * S;
+    const float Sh = h16((float)S);
+    x_ = h16(h16(G[5] - G[7]) / Sh);   // (r[2,1] - r[1,2]) / S with r = G.T
+    y_ = h16(h16(G[6] - G[2]) / Sh);
+    z_ = h16(h16(G[1] - G[3]) / Sh);
+  } else {
+    // large-rotation branches (never reached inside the locomotion envelope): evaluate in double
+    const double r00 = G[0], r11 = G[4], r22 = G[8];
+    double S, xx, yy, zz;
+    if (r00 > r11 && r00 > r22) { S = sqrt(1.0 + r00 - r11 - r22) * 2; wd = (G[5] - G[7]) / S; xx = 0.25 * S; yy = (G[3] + G[1]) / S; zz = (G[6] + G[2]) / S; }
+    else if (r11 > r22) { S = sqrt(1.0 + r11 - r00 - r22) * 2; wd = (G[6] - G[2]) / S; xx = (G[3] + G[1]) / S; yy = 0.25 * S; zz = (G[7] + G[5]) / S; }
+    else { S = sqrt(1.0 + r22 - r00 - r11) * 2; wd = (G[1] - G[3]) / S; xx = (G[6] + G[2]) / S; yy = (G[7] + G[5]) / S; zz = 0.25 * S; }
+    x_ = h16((float)xx); y_ = h16((float)yy); z_ = h16((float)zz);
+  }
+  w_ = h16((float)wd);   // a Python float next to float16 scalars is rounded to float16
+  const float as_arg = h16(-2.0f * h16(h16(x_ * z_) - h16(w_ * y_)));
+  const double as_ = (double)as_arg < 0.99999 ? (double)as_arg : 0.99999;
+  const float ww = h16((float)(wd * wd));
+  const float num0 = h16(2.0f * h16(h16(y_ * z_) + h16(w_ * x_)));
+  const float den0 = h16(h16(h16(ww - h16(x_ * x_)) - h16(y_ * y_)) + h16(z_ * z_));
+  const float num2 = h16(2.0f * h16(h16(x_ * y_) + h16(w_ * z_)));
+  const float den2 = h16(h16(h16(ww + h16(x_ * x_)) - h16(y_ * y_)) - h16(z_ * z_));
+  est[MPC_EST_RPYBODY + 0] = h16(atan2f(num0, den0));
+  est[MPC_EST_RPYBODY + 1] = round_f16(asin(as_));
+  est[MPC_EST_RPYBODY + 2] = h16(atan2f(num2, den2));
+}
 
 // per-leg scratch in shared memory (floats)
 enum { LG_Q = 0, LG_QD = 3, LG_P = 6, LG_J = 9, LG_V = 18, LG_PFOOT = 21, LG_FOOT = 24, LG_CONTACT = 27,

@@ -2,8 +2,8 @@
 
 Replaces the host loop ``for idx, controller in enumerate(self.controllers): controller.run(...)``
 (reference/RL_Environment/tasks/aliengo.py:252-256) — i.e. ``RobotRunnerMin.run``
-(robot_runner/RobotRunnerMin.py:54-76) minus ``StateEstimator.update`` — by ONE kernel launch
-per control tick: leg FK/Jacobian, gait phases and horizon table, CoM height / ground normal,
+(robot_runner/RobotRunnerMin.py:54-76) — by ONE kernel launch per control tick:
+StateEstimator.update (float16 rotations reproduced bit for bit), leg FK/Jacobian, gait phases and horizon table, CoM height / ground normal,
 foot placement, swing Bezier, QP marshalling, the OSQP-faithful QP solve when the MPC is due,
 and the Cartesian-PD + J^T f torque map.  All per-robot controller state
 (iterationCounter, firstSwing, swing trajectories, f_ff, estimator height / contact phase /
@@ -52,18 +52,23 @@ class BatchedLocomotion:
         else:
             self.state[idx] = self._fresh[idx]
 
-    def run(self, dof_state: torch.Tensor, est: torch.Tensor, commands: torch.Tensor, has_weights: bool = True,
+    def run(self, dof_state: torch.Tensor, root_states: torch.Tensor | None, commands: torch.Tensor,
+            has_weights: bool = True, est: torch.Tensor | None = None,
             records_out: torch.Tensor | None = None) -> torch.Tensor:
-        """One control tick.  ``dof_state`` [N,12,2] (pos, vel), ``est`` [N,18] (vBody, omegaBody,
-        rpyBody, ground_R_body row-major — StateEstimator.update outputs), ``commands`` [N,16]
-        (vx, vy, yaw rate, 13 weights).  Returns ``torques`` [N,12] (float32, device)."""
-        for t, shape in ((dof_state, (self.n, 12, 2)), (est, (self.n, 18)), (commands, (self.n, 16))):
+        """One control tick = ``RobotRunnerMin.run`` for every robot.  ``dof_state`` [N,12,2] (pos,
+        vel) and ``root_states`` [N,13] (pos, quat xyzw, lin vel, ang vel) are the Isaac Gym tensors
+        of ``pre_physics_step`` (aliengo.py:247-251); ``commands`` [N,16] = vx, vy, yaw rate, 13
+        weights.  Alternatively pass ``root_states=None`` and precomputed ``est`` [N,18]
+        (StateEstimator.update outputs).  Returns ``torques`` [N,12] (float32, device)."""
+        assert (root_states is None) != (est is None), "give exactly one of root_states / est"
+        src, shape2 = (root_states, (self.n, 13)) if est is None else (est, (self.n, 18))
+        for t, shape in ((dof_state, (self.n, 12, 2)), (src, shape2), (commands, (self.n, 16))):
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            rc = _lib.lib().mpc_b200_tick(C.byref(self.settings), C.byref(self.tick_params), p(dof_state), p(est),
-                                          p(commands), int(has_weights), p(self.gait), p(self.robot_params),
+            rc = _lib.lib().mpc_b200_tick(C.byref(self.settings), C.byref(self.tick_params), p(dof_state),
+                                          p(root_states), p(est), p(commands), int(has_weights), p(self.gait), p(self.robot_params),
                                           p(self.robot_geom), p(self.robot_type), self.n, p(self.state),
                                           p(self.torques), p(self.grf0), p(records_out), p(self.solved),
                                           C.c_void_p(stream))

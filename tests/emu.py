@@ -86,11 +86,14 @@ class TickParams(C.Structure):
 
 
 def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robot_type, flat_ground=False,
-         params=None, dt=0.01, iters_between_mpc=2):
-    """One emulated control tick; `state` [N,96] float32 is updated in place."""
+         params=None, dt=0.01, iters_between_mpc=2, body=None):
+    """One emulated control tick; `state` [N,96] float32 is updated in place.  Pass `body`
+    ([N,13] root states) with est=None to run StateEstimator.update in the emulated kernel."""
     n = state.shape[0]
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-    dof, est, cmd, rp, geom = f32(dof), f32(est), f32(cmd), f32(robot_params), f32(robot_geom)
+    dof, cmd, rp, geom = f32(dof), f32(cmd), f32(robot_params), f32(robot_geom)
+    est = None if est is None else f32(est)
+    body = None if body is None else f32(body)
     gait = np.ascontiguousarray(gait, dtype=np.int32)
     rt = np.ascontiguousarray(robot_type, dtype=np.int32)
     assert state.dtype == np.float32 and state.flags.c_contiguous
@@ -101,7 +104,9 @@ def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robo
     records = np.zeros((n, 96), np.float32)
     solved = np.zeros(n, np.int32)
     P = C.c_void_p
-    rc = lib().mpc_emu_tick(C.byref(prm), C.byref(tp), P(dof.ctypes.data), P(est.ctypes.data), P(cmd.ctypes.data),
+    rc = lib().mpc_emu_tick(C.byref(prm), C.byref(tp), P(dof.ctypes.data),
+                            P(body.ctypes.data) if body is not None else None,
+                            P(est.ctypes.data) if est is not None else None, P(cmd.ctypes.data),
                             int(has_weights), P(gait.ctypes.data), P(rp.ctypes.data), P(geom.ctypes.data),
                             P(rt.ctypes.data), n, P(state.ctypes.data), P(torques.ctypes.data), P(grf0.ctypes.data),
                             P(records.ctypes.data), P(solved.ctypes.data))

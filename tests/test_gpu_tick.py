@@ -20,10 +20,12 @@ def _gpu_tick_fn():
         loco.state.copy_(torch.from_numpy(state))
         rec = torch.zeros((1, 96), dtype=torch.float32, device="cuda:0")
         loco.solved.zero_()
-        tau = loco.run(torch.from_numpy(np.ascontiguousarray(dof, np.float32).reshape(1, 12, 2)).cuda(),
-                       torch.from_numpy(np.ascontiguousarray(est, np.float32)).cuda(),
-                       torch.from_numpy(np.ascontiguousarray(cmd, np.float32)).cuda(), has_weights=bool(with_w),
-                       records_out=rec)
+        t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+        if isinstance(est, tuple):
+            kw = dict(root_states=t32(est[1]))
+        else:
+            kw = dict(root_states=None, est=t32(est))
+        tau = loco.run(t32(dof).reshape(1, 12, 2), commands=t32(cmd), has_weights=bool(with_w), records_out=rec, **kw)
         torch.cuda.synchronize()
         state[:] = loco.state.cpu().numpy()
         return dict(torques=tau.cpu().numpy(), grf0=loco.grf0.cpu().numpy(), records=rec.cpu().numpy(),
@@ -31,10 +33,11 @@ def _gpu_tick_fn():
     return fn
 
 
+@pytest.mark.parametrize("device_estimator", [False, True])
 @pytest.mark.parametrize("name", ["aliengo_trot", "aliengo_walk_flat", "a1_bound"])
-def test_gpu_tick_replay_matches_reference_python(name):
+def test_gpu_tick_replay_matches_reference_python(name, device_estimator):
     from test_tick import replay
-    w = replay(name, _gpu_tick_fn())
+    w = replay(name, _gpu_tick_fn(), device_estimator)
     print(name, w)
     assert w["rec"] < 5e-6 and w["z"] < 1e-6 and w["fff"] < 5e-3 and w["tau"] < 2e-3
 
@@ -57,12 +60,12 @@ def test_batched_tick_equals_single_robot_ticks():
         est[:, 9:18] = np.eye(3).reshape(9)
         cmd = np.zeros((n, 16), np.float32)
         cmd[:, 0] = 0.5
-        tau = big.run(torch.from_numpy(dof).cuda(), torch.from_numpy(est).cuda(), torch.from_numpy(cmd).cuda(),
-                      has_weights=False).cpu().numpy().copy()
+        tau = big.run(torch.from_numpy(dof).cuda(), None, torch.from_numpy(cmd).cuda(), has_weights=False,
+                      est=torch.from_numpy(est).cuda()).cpu().numpy().copy()
         outs.append((dof, est, cmd, tau))
     for r in (0, 17, 95):
         one = BatchedLocomotion([rtype[r]], [gait[r]], device="cuda:0")
         for dof, est, cmd, tau in outs:
-            t1 = one.run(torch.from_numpy(dof[r:r + 1]).cuda(), torch.from_numpy(est[r:r + 1]).cuda(),
-                         torch.from_numpy(cmd[r:r + 1]).cuda(), has_weights=False).cpu().numpy()
+            t1 = one.run(torch.from_numpy(dof[r:r + 1]).cuda(), None, torch.from_numpy(cmd[r:r + 1]).cuda(),
+                         has_weights=False, est=torch.from_numpy(est[r:r + 1]).cuda()).cpu().numpy()
             assert np.array_equal(t1[0], tau[r])

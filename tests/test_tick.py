@@ -14,7 +14,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _ORDER = {RobotType.ALIENGO: 1, RobotType.A1: 2, RobotType.GO1: 3}   # reference enum auto() values
 
 
-def replay(name, tick_fn):
+def replay(name, tick_fn, device_estimator=False):
     g = np.load(os.path.join(GOLD, f"tick_golden_{name}.npz"))
     ref_robot, gait, flat, with_w = [int(v) for v in g["meta"]]
     rtype = {v: k for k, v in _ORDER.items()}[ref_robot]
@@ -22,6 +22,8 @@ def replay(name, tick_fn):
     worst = dict(tau=0.0, rec=0.0, fff=0.0, z=0.0)
     for t in range(len(g["dof"])):
         est = np.concatenate([g["vBody"][t], g["omegaBody"][t], g["rpyBody"][t], g["groundR"][t]])[None]
+        if device_estimator:   # raw root states in, StateEstimator.update runs inside the kernel
+            est = ("body", g["body"][t][None])
         out = tick_fn(state, g["dof"][t][None], est, g["cmd"][t][None], with_w, [gait], [int(rtype)], flat)
         assert int(state.view(np.int32)[0, 0]) == int(g["counter"][t])
         assert bool(out["solved"][0] == 1) == bool(g["solved"][t])
@@ -37,14 +39,37 @@ def replay(name, tick_fn):
 
 
 def _emu_tick(state, dof, est, cmd, with_w, gait, rtype, flat):
+    if isinstance(est, tuple):
+        return emu.tick(state, dof, None, cmd, with_w, gait, params_table(), geom_table(), rtype, flat_ground=flat,
+                        body=est[1])
     return emu.tick(state, dof, est, cmd, with_w, gait, params_table(), geom_table(), rtype, flat_ground=flat)
 
 
+@pytest.mark.parametrize("device_estimator", [False, True])
 @pytest.mark.parametrize("name", ["aliengo_trot", "aliengo_walk_flat", "a1_bound"])
-def test_tick_replay_matches_reference_python(name):
-    w = replay(name, _emu_tick)
+def test_tick_replay_matches_reference_python(name, device_estimator):
+    w = replay(name, _emu_tick, device_estimator)
     print(name, w)
     assert w["rec"] < 5e-6       # QP arguments (float32 marshalling, fp32 estimator arithmetic)
     assert w["z"] < 1e-6
     assert w["fff"] < 5e-3       # MPC forces [N]: the QP inputs differ in the last float32 bits
     assert w["tau"] < 2e-3       # joint torques [N m]
+
+
+def test_device_estimator_reproduces_float16_outputs_bit_for_bit():
+    """StateEstimator.update restated with the reference's float16/float32 mix: rpyBody and
+    ground_R_body_frame (float16 in the reference) must be EXACT, body-frame velocities 1e-6."""
+    import ctypes as C
+    L = emu.lib()
+    for name in ("aliengo_trot", "aliengo_walk_flat", "a1_bound"):
+        g = np.load(os.path.join(GOLD, f"tick_golden_{name}.npz"))
+        T = len(g["body"])
+        body = np.ascontiguousarray(g["body"], np.float32)
+        normal = np.zeros((T, 3), np.float32)
+        normal[0] = [0, 0, 1]
+        normal[1:] = g["normal"][:-1]
+        est = np.zeros((T, 18), np.float32)
+        L.mpc_emu_estimator(C.c_void_p(body.ctypes.data), C.c_void_p(normal.ctypes.data), C.c_void_p(est.ctypes.data), T)
+        assert np.array_equal(est[:, 6:9], g["rpyBody"].astype(np.float32))
+        assert np.array_equal(est[:, 9:18], g["groundR"].astype(np.float32))
+        assert np.abs(est[:, 0:3] - g["vBody"]).max() < 1e-6 and np.abs(est[:, 3:6] - g["omegaBody"]).max() < 1e-6

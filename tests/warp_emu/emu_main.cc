@@ -39,7 +39,7 @@ extern "C" int mpc_emu_solve(const float* rec, int n, int horizon, const float* 
 
 // One emulated control tick for n robots (same sequence as mpc_tick_kernel in mpc_b200.cu).
 extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParams* tp, const float* dof,
-                            const float* est, const float* cmd, int has_weights, const int* gait,
+                            const float* body, const float* est, const float* cmd, int has_weights, const int* gait,
                             const float* rp, const float* geom, const int* rt, int n, float* state,
                             float* torques, float* grf0, float* records, int32_t* solved) {
   constexpr int H = 10;
@@ -58,7 +58,9 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     int32_t st_code = 0;
     float* st = state + (size_t)r * MPC_TICK_STATE_STRIDE;
     const float* g = geom + (size_t)type * MPC_GEOM_STRIDE;
-    const float* e = est + (size_t)r * MPC_EST_STRIDE;
+    float est_local[MPC_EST_STRIDE];
+    const float* e = est ? est + (size_t)r * MPC_EST_STRIDE : est_local;
+    if (!est) mpc::estimator_update(body + (size_t)r * 13, st + MPC_ST_NORMAL, est_local);
     const int do_solve = mpc::tick_pre<H>(dof + (size_t)r * 24, e, cmd + (size_t)r * MPC_CMD_STRIDE, has_weights,
                                           gait ? gait[r] : 0, g, *tp, st, rec, legs);
     if (records) std::memcpy(records + (size_t)r * stride, rec, sizeof(rec));
@@ -72,4 +74,8 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     if (solved) solved[r] = st_code;
   }
   return 0;
+}
+
+extern "C" void mpc_emu_estimator(const float* body, const float* normal, float* est, int n) {
+  for (int r = 0; r < n; ++r) mpc::estimator_update(body + 13 * r, normal + 3 * r, est + MPC_EST_STRIDE * r);
 }
