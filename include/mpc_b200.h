@@ -51,6 +51,10 @@ extern "C" {
 
 #define MPC_B200_MAX_HORIZON 16
 
+/* per-robot OSQP workspace state carried between consecutive solves (float64):
+ * valid flag, rho, x[12h], z[20h], y[20h] (scaled iterates), previous unscaled q[12h]        */
+#define MPC_WARM_STRIDE(h)  (2 + 64 * (h))
+
 /* error codes */
 #define MPC_B200_OK            0
 #define MPC_B200_EINVAL       -1   /* bad argument (null ptr, horizon, ...)  */
@@ -119,6 +123,10 @@ int  mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta,
  *   d_resid        [n_robots, 2] float32 device or NULL (primal, dual residual)
  *   d_info         [n_robots, 8] float64 device or NULL: iterations, rho updates,
  *                  final rho, polish status, pri_res, dua_res, cost scale, n_free
+ *   d_warm         [n_robots, MPC_WARM_STRIDE(h)] float64 device or NULL: OSQP's persistent
+ *                  workspace state (settings.warm_start = true, mpc_osqp.cc:708, :760-778).
+ *                  Rows with flag 0 start cold (= osqp_setup on the first call); every solve
+ *                  leaves its iterates / rho / q for the next one.  NULL = cold start always.
  *   stream         cudaStream_t as void* (NULL = legacy default stream)
  * Asynchronous w.r.t. the host.
  */
@@ -132,6 +140,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings,
                          int32_t* d_status,
                          float* d_resid,
                          double* d_info,
+                         double* d_warm,
                          void* stream);
 
 /*
@@ -217,13 +226,14 @@ typedef struct MpcB200TickParams {
  *   d_grf0   [n, 12] float32 out or NULL: written for robots whose MPC fired this tick
  *   d_records[n, MPC_REC_STRIDE(h)] float32 out or NULL: the QP record built this tick (tests)
  *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise
+ *   d_warm   [n, MPC_WARM_STRIDE(h)] float64 in/out or NULL: see mpc_b200_solve_batch
  */
 int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick,
                   const float* d_dof, const float* d_body, const float* d_est, const float* d_cmd,
                   int has_weights,
                   const int32_t* d_gait, const float* d_robot_params, const float* d_robot_geom,
                   const int32_t* d_robot_type, int n_robots, float* d_state, float* d_torques,
-                  float* d_grf0, float* d_records, int32_t* d_solved, void* stream);
+                  float* d_grf0, float* d_records, int32_t* d_solved, double* d_warm, void* stream);
 
 /* Debug / test hook: run ONE record through the solve kernel and copy back the
  * quantities the kernel never materialises in production: the dense Hessian

@@ -59,14 +59,14 @@ def lib():
         L.mpc_b200_device_count.restype = C.c_int
         L.mpc_b200_kernel_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.mpc_b200_kernel_info.restype = C.c_int
-        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_solve_batch.restype = C.c_int
         L.mpc_b200_solve_batch_host.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp]
         L.mpc_b200_solve_batch_host.restype = C.c_int
         L.mpc_b200_debug_build_qp.argtypes = [C.POINTER(Settings), vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_debug_build_qp.restype = C.c_int
         L.mpc_b200_tick.argtypes = [C.POINTER(Settings), C.POINTER(TickParams), vp, vp, vp, vp, C.c_int, vp, vp, vp,
-                                    vp, C.c_int, vp, vp, vp, vp, vp, vp]
+                                    vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tick.restype = C.c_int
         _lib = L
     return _lib

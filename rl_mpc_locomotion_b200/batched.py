@@ -36,8 +36,15 @@ class BatchedConvexMpc:
         self.robot_params = torch.from_numpy(np.ascontiguousarray(rp)).to(self.device)
         self.stride = rec_stride(horizon)
 
+    def warm_buffer(self, n: int) -> torch.Tensor:
+        """Fresh (all-cold) OSQP workspace-state tensor for `n` robots: pass it as ``warm=`` to
+        consecutive solves of the same robots to get the reference's ``warm_start`` behaviour
+        (mpc_osqp.cc:708, :760-778); zero a row to force ``osqp_setup`` semantics for that robot."""
+        return torch.zeros((n, 2 + 64 * self.horizon), dtype=torch.float64, device=self.device)
+
     def solve(self, records: torch.Tensor, robot_type: torch.Tensor | None = None, *, full: bool = False,
-              status: bool = True, info: bool = False, out: torch.Tensor | None = None) -> dict:
+              status: bool = True, info: bool = False, out: torch.Tensor | None = None,
+              warm: torch.Tensor | None = None) -> dict:
         """``records`` [N, stride] float32 CUDA tensor -> dict(grf0[N,12], grf_full?, status?, resid, info?).
 
         ``grf0`` is the negated horizon-0 QP solution, i.e. exactly ``result[0:12]`` of the
@@ -57,11 +64,14 @@ class BatchedConvexMpc:
         inf = torch.empty((n, 8), dtype=torch.float64, device=dev) if info else None
         if robot_type is not None:
             assert robot_type.is_cuda and robot_type.dtype == torch.int32 and robot_type.shape == (n,)
+        if warm is not None:
+            assert warm.is_cuda and warm.dtype == torch.float64 and warm.is_contiguous()
+            assert tuple(warm.shape) == (n, 2 + 64 * self.horizon), warm.shape
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = _lib.lib().mpc_b200_solve_batch(C.byref(self.settings), ptr(records), ptr(self.robot_params),
                                                  ptr(robot_type), n, ptr(grf0), ptr(gfull), ptr(st),
-                                                 ptr(resid), ptr(inf), C.c_void_p(stream))
+                                                 ptr(resid), ptr(inf), ptr(warm), C.c_void_p(stream))
         _lib.check(rc, "mpc_b200_solve_batch")
         if full:
             res["grf_full"] = gfull

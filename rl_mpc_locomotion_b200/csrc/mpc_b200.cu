@@ -85,7 +85,7 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                  const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
                  int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
                  int32_t* __restrict__ status, float* __restrict__ resid, double* __restrict__ info,
-                 double* __restrict__ dbg) {
+                 double* __restrict__ dbg, double* __restrict__ warm) {
   using K = KernelCfg<H>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -113,7 +113,8 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                       grf_full ? grf_full + (size_t)robot * 12 * H : nullptr,
                       status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
                       info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr,
-                      dbg ? dbg + (size_t)robot * dbg_stride : nullptr, lane);
+                      dbg ? dbg + (size_t)robot * dbg_stride : nullptr,
+                      warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
 }
 
 
@@ -137,7 +138,7 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
                 const int32_t* __restrict__ gait, const float* __restrict__ robot_params,
                 const float* __restrict__ robot_geom, const int32_t* __restrict__ robot_type, int n_robots,
                 float* __restrict__ state, float* __restrict__ torques, float* __restrict__ grf0,
-                float* __restrict__ records, int32_t* __restrict__ solved) {
+                float* __restrict__ records, int32_t* __restrict__ solved, double* __restrict__ warm) {
   using K = KernelCfg<H>;
   using T = TickCfg<H>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -177,7 +178,8 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) records[(size_t)robot * K::REC_FLOATS + i] = rec_s[i];
   if (do_solve) {
     mpc::fill_tables<H>(sm, prm.dt, lane);
-    mpc::solve_robot<H>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, nullptr, nullptr, lane);
+    mpc::solve_robot<H>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, nullptr, nullptr,
+                        warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
     __syncthreads();
     if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
   }
@@ -190,7 +192,7 @@ template <int H>
 int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* body,
                 const float* est, const float* cmd, int has_weights, const int32_t* gait, const float* rp, const float* geom,
                 const int32_t* rt, int n, float* state, float* torques, float* grf0, float* records,
-                int32_t* solved, cudaStream_t stream) {
+                int32_t* solved, double* warm, cudaStream_t stream) {
   using T = TickCfg<H>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -200,7 +202,7 @@ int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const fl
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem, tick)");
   if (n <= 0) return MPC_B200_OK;
   mpc_tick_kernel<H><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp, geom, rt, n,
-                                                         state, torques, grf0, records, solved);
+                                                         state, torques, grf0, records, solved, warm);
   CK(cudaGetLastError());
   return MPC_B200_OK;
 }
@@ -253,7 +255,7 @@ int check_settings(const MpcB200Settings* s) {
 
 template <int H>
 int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n,
-           float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg,
+           float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
            cudaStream_t stream) {
   using K = KernelCfg<H>;
   static std::once_flag once;
@@ -265,17 +267,18 @@ int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
   if (n <= 0) return MPC_B200_OK;
   mpc_solve_kernel<H><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status, resid,
-                                                       info, dbg);
+                                                           info, dbg, warm);
   CK(cudaGetLastError());
   return MPC_B200_OK;
 }
 
 int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int n,
-             float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg,
+             float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
              cudaStream_t stream) {
   const mpc::SolveParams prm = to_params(*s);
-  if (s->horizon == 10) return launch<10>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, stream);
-  return launch<16>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, stream);
+  if (s->horizon == 10)
+    return launch<10>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, stream);
+  return launch<16>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, stream);
 }
 
 // grow-only device scratch for the host-pointer convenience entry points
@@ -355,7 +358,7 @@ int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int*
 int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records,
                          const float* d_robot_params, const int32_t* d_robot_type, int n_robots,
                          float* d_grf0, float* d_grf_full, int32_t* d_status, float* d_resid,
-                         double* d_info, void* stream) {
+                         double* d_info, double* d_warm, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
   if (n_robots < 0 || (n_robots > 0 && (!d_records || !d_robot_params || !d_grf0))) {
@@ -368,7 +371,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records
   }
   if (n_robots == 0) return MPC_B200_OK;
   return dispatch(settings, d_records, d_robot_params, d_robot_type, n_robots, d_grf0, d_grf_full, d_status,
-                  d_resid, d_info, nullptr, (cudaStream_t)stream);
+                  d_resid, d_info, nullptr, d_warm, (cudaStream_t)stream);
 }
 
 int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_records,
@@ -411,7 +414,7 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_re
                      cudaMemcpyHostToDevice, st));
   if (h_robot_type) CK(cudaMemcpyAsync(d_rt, h_robot_type, (size_t)n_robots * 4, cudaMemcpyHostToDevice, st));
   rc = dispatch(settings, d_rec, d_rp, h_robot_type ? d_rt : nullptr, n_robots, d_g0,
-                h_grf_full ? d_gf : nullptr, h_status ? d_st : nullptr, nullptr, nullptr, nullptr, st);
+                h_grf_full ? d_gf : nullptr, h_status ? d_st : nullptr, nullptr, nullptr, nullptr, nullptr, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_grf0, d_g0, (size_t)n_robots * 12 * 4, cudaMemcpyDeviceToHost, st));
   if (h_grf_full) CK(cudaMemcpyAsync(h_grf_full, d_gf, (size_t)n_robots * 12 * h * 4, cudaMemcpyDeviceToHost, st));
@@ -425,7 +428,7 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
                   const int32_t* d_gait,
                   const float* d_robot_params, const float* d_robot_geom, const int32_t* d_robot_type,
                   int n_robots, float* d_state, float* d_torques, float* d_grf0, float* d_records,
-                  int32_t* d_solved, void* stream) {
+                  int32_t* d_solved, double* d_warm, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
   if (!tick || tick->iters_between_mpc <= 0 || !(tick->dt > 0)) {
@@ -454,9 +457,9 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
   cudaStream_t st = (cudaStream_t)stream;
   if (settings->horizon == 10)
     return launch_tick<10>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
-                           d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, st);
+                           d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, st);
   return launch_tick<16>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
-                         d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, st);
+                         d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, st);
 }
 
 int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_record,
@@ -478,7 +481,7 @@ int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_reco
   CK(cudaMalloc(&d_dbg, ndbg * 8));
   CK(cudaMemcpy(d_rec, h_record, MPC_REC_STRIDE(h) * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_rp, h_robot_params, MPC_ROBOT_PARAMS_STRIDE * 4, cudaMemcpyHostToDevice));
-  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr);
+  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr, nullptr);
   if (rc == MPC_B200_OK) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = cuda_fail(e, "debug kernel");

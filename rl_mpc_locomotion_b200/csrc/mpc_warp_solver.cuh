@@ -212,12 +212,19 @@ MPC_FN void fill_tables(double* sm, double dt
 template <int H>
 MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& prm, double* sm,
                         float* grf0, float* grf_full, int32_t* status_out, float* resid_out,
-                        double* info_out, double* dbg_out
+                        double* info_out, double* dbg_out, double* warm
 #if defined(__CUDACC__) && !defined(MPC_EMULATE)
                         , const int lane
 #endif
 ) {
   using D = Dims<H>;
+  // `warm` (MPC_WARM_STRIDE(H) doubles in global memory, or null): OSQP's persistent workspace
+  // state between consecutive solves of the same robot (settings.warm_start, mpc_osqp.cc:708,
+  // :760-778): [0] valid flag, [1] rho, then x[12h], z[20h], y[20h] (scaled iterates, left as
+  // they are when the data is re-scaled, exactly as osqp_update_P_A does) and the previous
+  // UNSCALED q[12h] (osqp_update_P_A re-runs scale_data before osqp_update_lin_cost installs the
+  // new q, so the cost normalisation c sees the OLD q).
+  const bool warm_valid = warm != nullptr && warm[0] != 0.0;
   constexpr int NS = D::NSLOT, NW = D::NW, NV = D::NV, NRS = D::NRS;
   double* const Wp = sm + D::OFF_WP;
   double* const vecA = sm + D::OFF_VECA;
@@ -259,6 +266,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   PER_LANE_ARR(double, zv, [NS][5]);
   PER_LANE_ARR(double, yv, [NS][5]);
   PER_LANE_ARR(double, qb, [NS][3]);   // scaled linear cost
+  PER_LANE_ARR(double, qnew, [NS][3]); // unscaled linear cost of THIS problem
   PER_LANE_ARR(double, Dv, [NS][3]);   // Ruiz D
   PER_LANE_ARR(double, Ev, [NS][5]);   // Ruiz E
   PER_LANE_ARR(double, di, [NS][6]);   // Delta^-1 (sym 3x3)
@@ -451,6 +459,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
       for (int c = 0; c < 6; ++c) q += _(wbl)[c][a] * vt[6 * k + c];
       _(qb)[s][a] = _(valid)[s] ? 2.0 * q : 0.0;
+      _(qnew)[s][a] = _(qb)[s][a];
+      if (warm_valid && _(valid)[s]) _(qb)[s][a] = warm[2 + 52 * H + 3 * j + a];   // scale with the OLD q
       _(Dv)[s][a] = 1.0;
       _(xv)[s][a] = 0.0;
     }
@@ -470,7 +480,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s])
 #pragma unroll
-        for (int a = 0; a < 3; ++a) dbg_out[3 * (lane + NL * s) + a] = _(qb)[s][a];
+        for (int a = 0; a < 3; ++a) dbg_out[3 * (lane + NL * s) + a] = _(qnew)[s][a];
     LANES_END
   }
 
@@ -981,6 +991,27 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 
   // ------------------------------------------------------------------ S3: rho, factor
   double rho = fmin(fmax(prm.rho0, kRhoMin), kRhoMax);  // auxil.c:82
+  if (warm_valid) {
+    rho = warm[1];   // settings->rho keeps the value adapted during the previous solve
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + NL * s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          // osqp_update_lin_cost: q = c * (D .* q_new)   (osqp.c:752-782)
+          _(qb)[s][a] = (_(Dv)[s][a] * _(qnew)[s][a]) * cscale;
+          _(xv)[s][a] = warm[2 + 3 * j + a];
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          _(zv)[s][r] = warm[2 + 12 * H + 5 * j + r];
+          _(yv)[s][r] = warm[2 + 32 * H + 5 * j + r];
+        }
+      }
+    LANES_END
+  }
   LANES_BEGIN
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
@@ -1554,6 +1585,27 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         if (j < 4) grf0[3 * j + a] = f;
         if (grf_full) grf_full[3 * j + a] = f;
       }
+    }
+  }
+  if (warm) {   // leave the workspace state for the next solve (scaled iterates, rho, unscaled q)
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + NL * s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          warm[2 + 3 * j + a] = _(xv)[s][a];
+          warm[2 + 52 * H + 3 * j + a] = _(qnew)[s][a];
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          warm[2 + 12 * H + 5 * j + r] = _(zv)[s][r];
+          warm[2 + 32 * H + 5 * j + r] = _(yv)[s][r];
+        }
+      }
+    if (lane == 0) {
+      warm[0] = 1.0;
+      warm[1] = rho;
     }
   }
   if (lane == 0) {

@@ -23,7 +23,7 @@ from .robots import TICK_STATE_STRIDE, geom_table, initial_tick_state, params_ta
 
 class BatchedLocomotion:
     def __init__(self, robot_type, gait, horizon: int = 10, device="cuda", dt: float = 0.01,
-                 iters_between_mpc: int = 2, flat_ground: bool = False, **settings):
+                 iters_between_mpc: int = 2, flat_ground: bool = False, warm_start: bool = False, **settings):
         """``robot_type`` / ``gait``: per-robot int arrays (RobotType values; gait ids as in
         ConvexMPCLocomotion.run :227-241 — the reference can only express ONE global gait,
         Parameters.cmpc_gait)."""
@@ -44,13 +44,23 @@ class BatchedLocomotion:
         self.torques = torch.empty((self.n, 12), dtype=torch.float32, device=dev)
         self.grf0 = torch.zeros((self.n, 12), dtype=torch.float32, device=dev)
         self.solved = torch.zeros((self.n,), dtype=torch.int32, device=dev)
+        # OSQP workspace state per robot: the reference's OSQP branch keeps one workspace per
+        # ConvexMpc object and warm-starts every tick (mpc_osqp.cc:757-778); off by default
+        # (cold start = the golden-vector semantics)
+        self.warm = torch.zeros((self.n, 2 + 64 * horizon), dtype=torch.float64, device=dev) if warm_start else None
 
     def reset(self, idx=None):
-        """``controller.reset()`` for the given robots (aliengo.py:333-334); all when None."""
+        """``controller.reset()`` for the given robots (aliengo.py:333-334); all when None.
+        ``ConvexMPCLocomotion.initialize`` builds a new ``ConvexMpc`` (ConvexMPCLocomotion.py:102),
+        so the OSQP workspace state is dropped too."""
         if idx is None:
             self.state.copy_(self._fresh)
+            if self.warm is not None:
+                self.warm.zero_()
         else:
             self.state[idx] = self._fresh[idx]
+            if self.warm is not None:
+                self.warm[idx] = 0
 
     def run(self, dof_state: torch.Tensor, root_states: torch.Tensor | None, commands: torch.Tensor,
             has_weights: bool = True, est: torch.Tensor | None = None,
@@ -71,6 +81,6 @@ class BatchedLocomotion:
                                           p(root_states), p(est), p(commands), int(has_weights), p(self.gait), p(self.robot_params),
                                           p(self.robot_geom), p(self.robot_type), self.n, p(self.state),
                                           p(self.torques), p(self.grf0), p(records_out), p(self.solved),
-                                          C.c_void_p(stream))
+                                          p(self.warm), C.c_void_p(stream))
         _lib.check(rc, "mpc_b200_tick")
         return self.torques

@@ -52,7 +52,7 @@ def lib():
     return _lib
 
 
-def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg=False):
+def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg=False, warm=None):
     rec = np.ascontiguousarray(records, dtype=np.float32)
     n = rec.shape[0]
     rp = np.ascontiguousarray(robot_params, dtype=np.float32)
@@ -68,7 +68,8 @@ def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg
     rc = lib().mpc_emu_solve(P(rec.ctypes.data), n, horizon, P(rp.ctypes.data),
                              P(rt.ctypes.data) if rt is not None else None, C.byref(prm),
                              P(grf0.ctypes.data), P(full.ctypes.data), P(status.ctypes.data),
-                             P(info.ctypes.data), P(dbg.ctypes.data) if dbg is not None else None)
+                             P(info.ctypes.data), P(dbg.ctypes.data) if dbg is not None else None,
+                             P(warm.ctypes.data) if warm is not None else None)
     assert rc == 0
     out = dict(grf0=grf0, grf_full=full, status=status, info=info)
     if want_dbg:
@@ -86,7 +87,7 @@ class TickParams(C.Structure):
 
 
 def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robot_type, flat_ground=False,
-         params=None, dt=0.01, iters_between_mpc=2, body=None):
+         params=None, dt=0.01, iters_between_mpc=2, body=None, warm=None):
     """One emulated control tick; `state` [N,96] float32 is updated in place.  Pass `body`
     ([N,13] root states) with est=None to run StateEstimator.update in the emulated kernel."""
     n = state.shape[0]
@@ -109,6 +110,7 @@ def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robo
                             P(est.ctypes.data) if est is not None else None, P(cmd.ctypes.data),
                             int(has_weights), P(gait.ctypes.data), P(rp.ctypes.data), P(geom.ctypes.data),
                             P(rt.ctypes.data), n, P(state.ctypes.data), P(torques.ctypes.data), P(grf0.ctypes.data),
-                            P(records.ctypes.data), P(solved.ctypes.data))
+                            P(records.ctypes.data), P(solved.ctypes.data),
+                            P(warm.ctypes.data) if warm is not None else None)
     assert rc == 0
     return dict(torques=torques, grf0=grf0, records=records, solved=solved)

@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-os.environ["MPC_ORACLE_MODE"] = "cold"
+os.environ["MPC_ORACLE_MODE"] = "warm" if "--warm" in sys.argv else "cold"
 sys.path.insert(0, os.path.join(ROOT, "oracle"))   # provides `import mpc_osqp`
 sys.path.insert(0, "/root/reference")
 
@@ -109,6 +109,9 @@ def run_case(name, robot, gait, flat, ticks, seed, with_weights):
 
 
 if __name__ == "__main__":
+    if "--warm" in sys.argv:   # the reference's persistent OSQP workspace (warm start every tick)
+        run_case("aliengo_trot_warm", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True)
+        sys.exit(0)
     run_case("aliengo_trot", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True)
     run_case("aliengo_walk_flat", RobotType.ALIENGO, GaitType.WALK, True, 60, 2, False)
     run_case("a1_bound", RobotType.A1, GaitType.BOUND, False, 60, 3, True)

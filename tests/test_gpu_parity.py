@@ -112,3 +112,25 @@ def test_empty_and_single_batches():
     out1 = mpc.solve(torch.from_numpy(rec).cuda())
     torch.cuda.synchronize()
     assert out1["grf0"].shape == (1, 12) and int(out1["status"][0]) == 1
+
+
+def test_warm_start_sequence_on_device(oracle_mod):
+    """Consecutive solves of one robot through the persistent workspace-state buffer vs the
+    reference OSQP's warm-started workspace (same check as tests/test_warp_emu.py, on the GPU)."""
+    import torch
+    from test_warp_emu import _qp_sequence
+    from rl_mpc_locomotion_b200.batched import BatchedConvexMpc
+    from rl_mpc_locomotion_b200.records import unpack_record
+    from rl_mpc_locomotion_b200.robots import params_table
+    rec, _ = _qp_sequence("aliengo_trot")
+    params = params_table()
+    rp = params[0].astype(np.float64)
+    o = oracle_mod.OracleMpc(rp[0], rp[1:10], horizon=10)
+    mpc = BatchedConvexMpc(10, device="cuda:0", robot_params=params)
+    warm = mpc.warm_buffer(1)
+    for t in range(len(rec)):
+        st, f = o.solve(oracle_mod.WARM, **unpack_record(rec[t], 10))
+        out = mpc.solve(torch.from_numpy(rec[t:t + 1]).cuda(), full=True, info=True, warm=warm)
+        torch.cuda.synchronize()
+        assert int(out["info"][0, 0]) == o.last_iters and int(out["status"][0]) == st
+        assert np.abs(out["grf_full"][0].cpu().numpy() - f).max() < TOL_N

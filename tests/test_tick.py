@@ -14,7 +14,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _ORDER = {RobotType.ALIENGO: 1, RobotType.A1: 2, RobotType.GO1: 3}   # reference enum auto() values
 
 
-def replay(name, tick_fn, device_estimator=False):
+def replay(name, tick_fn, device_estimator=False, warm=None):
     g = np.load(os.path.join(GOLD, f"tick_golden_{name}.npz"))
     ref_robot, gait, flat, with_w = [int(v) for v in g["meta"]]
     rtype = {v: k for k, v in _ORDER.items()}[ref_robot]
@@ -24,7 +24,10 @@ def replay(name, tick_fn, device_estimator=False):
         est = np.concatenate([g["vBody"][t], g["omegaBody"][t], g["rpyBody"][t], g["groundR"][t]])[None]
         if device_estimator:   # raw root states in, StateEstimator.update runs inside the kernel
             est = ("body", g["body"][t][None])
-        out = tick_fn(state, g["dof"][t][None], est, g["cmd"][t][None], with_w, [gait], [int(rtype)], flat)
+        if warm is not None:
+            out = tick_fn(state, g["dof"][t][None], est, g["cmd"][t][None], with_w, [gait], [int(rtype)], flat, warm)
+        else:
+            out = tick_fn(state, g["dof"][t][None], est, g["cmd"][t][None], with_w, [gait], [int(rtype)], flat)
         assert int(state.view(np.int32)[0, 0]) == int(g["counter"][t])
         assert bool(out["solved"][0] == 1) == bool(g["solved"][t])
         if g["solved"][t]:
@@ -38,11 +41,12 @@ def replay(name, tick_fn, device_estimator=False):
     return worst
 
 
-def _emu_tick(state, dof, est, cmd, with_w, gait, rtype, flat):
+def _emu_tick(state, dof, est, cmd, with_w, gait, rtype, flat, warm=None):
     if isinstance(est, tuple):
         return emu.tick(state, dof, None, cmd, with_w, gait, params_table(), geom_table(), rtype, flat_ground=flat,
-                        body=est[1])
-    return emu.tick(state, dof, est, cmd, with_w, gait, params_table(), geom_table(), rtype, flat_ground=flat)
+                        body=est[1], warm=warm)
+    return emu.tick(state, dof, est, cmd, with_w, gait, params_table(), geom_table(), rtype, flat_ground=flat,
+                    warm=warm)
 
 
 @pytest.mark.parametrize("device_estimator", [False, True])
@@ -73,3 +77,12 @@ def test_device_estimator_reproduces_float16_outputs_bit_for_bit():
         assert np.array_equal(est[:, 6:9], g["rpyBody"].astype(np.float32))
         assert np.array_equal(est[:, 9:18], g["groundR"].astype(np.float32))
         assert np.abs(est[:, 0:3] - g["vBody"]).max() < 1e-6 and np.abs(est[:, 3:6] - g["omegaBody"]).max() < 1e-6
+
+
+def test_tick_replay_with_warm_started_osqp_workspace():
+    """The reference's OSQP branch keeps ONE workspace per robot and warm-starts every MPC tick
+    (mpc_osqp.cc:757-778); fixture recorded with the oracle module in WARM mode."""
+    warm = np.zeros((1, 2 + 64 * 10))
+    w = replay("aliengo_trot_warm", _emu_tick, device_estimator=True, warm=warm)
+    print(w)
+    assert w["rec"] < 5e-6 and w["fff"] < 5e-3 and w["tau"] < 2e-3

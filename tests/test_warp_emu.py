@@ -60,3 +60,39 @@ def test_fixed_iteration_mode_converges_to_true_minimiser(oracle_mod):
         out = emu.solve(rec, 10, params, rt, params=prm)
         errs.append(np.abs(out["grf_full"] - g["true_minimiser"][:24]).max(axis=1).mean())
     assert errs[2] < errs[1] < errs[0]
+
+
+def _qp_sequence(name):
+    """The QP problem records of the 30 consecutive MPC solves of a golden tick fixture."""
+    g = np.load(os.path.join(GOLD, f"tick_golden_{name}.npz"))
+    idx = np.nonzero(g["solved"])[0]
+    a = g["qp_args"][idx]
+    rec = np.concatenate([a[:, :28], a[:, 68:96], a[:, 28:68]], 1).astype(np.float32)   # argument -> record order
+    return rec, int(g["meta"][0])
+
+
+@pytest.mark.parametrize("name,rtype", [("aliengo_trot", 0), ("a1_bound", 1)])
+def test_warm_start_sequence_matches_reference_osqp_workspace(oracle_mod, name, rtype):
+    """settings.warm_start = true (mpc_osqp.cc:708): consecutive solves of one robot through ONE
+    persistent OSQP workspace (osqp_update_P_A / lin_cost / bounds, :760-778) vs our per-robot
+    workspace-state buffer: same iterates carried over, same adapted rho, same stale-q cost
+    normalisation."""
+    from rl_mpc_locomotion_b200.records import unpack_record
+    from rl_mpc_locomotion_b200.robots import params_table
+    rec, _ = _qp_sequence(name)
+    params = params_table()
+    rp = params[rtype].astype(np.float64)
+    o = oracle_mod.OracleMpc(rp[0], rp[1:10], horizon=10)
+    warm = np.zeros((1, 2 + 64 * 10))
+    cold_iters, warm_iters = [], []
+    for t in range(len(rec)):
+        st, f = o.solve(oracle_mod.WARM, **unpack_record(rec[t], 10))
+        out = emu.solve(rec[t:t + 1], 10, params, np.array([rtype], np.int32), warm=warm)
+        assert out["status"][0] == st == 1
+        assert int(out["info"][0, 0]) == o.last_iters, (t, out["info"][0, 0], o.last_iters)
+        assert int(out["info"][0, 3]) == o.last_polish_status
+        assert np.abs(out["grf_full"][0] - f).max() < 1e-3, (t, np.abs(out["grf_full"][0] - f).max())
+        warm_iters.append(o.last_iters)
+        cold_iters.append(int(emu.solve(rec[t:t + 1], 10, params, np.array([rtype], np.int32))["info"][0, 0]))
+    assert warm[0, 0] == 1.0
+    assert np.mean(warm_iters[1:]) < np.mean(cold_iters[1:])      # warm starts pay off

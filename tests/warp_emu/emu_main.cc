@@ -13,7 +13,7 @@
 
 template <int H>
 static void run(const float* rec, int n, const float* rp, const int* rt, const mpc::SolveParams& prm,
-                float* grf0, float* grf_full, int32_t* status, double* info, double* dbg) {
+                float* grf0, float* grf_full, int32_t* status, double* info, double* dbg, double* warm) {
   using D = mpc::Dims<H>;
   std::vector<double> sm(D::SMEM_DOUBLES, 0.0);
   mpc::fill_tables<H>(sm.data(), prm.dt);
@@ -24,15 +24,16 @@ static void run(const float* rec, int n, const float* rp, const int* rt, const m
     mpc::solve_robot<H>(rec + (size_t)r * stride, rpr, prm, sm.data(), grf0 + (size_t)r * 12,
                         grf_full ? grf_full + (size_t)r * 12 * H : nullptr, status ? status + r : nullptr,
                         nullptr, info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr,
-                        dbg ? dbg + (size_t)r * dbg_stride : nullptr);
+                        dbg ? dbg + (size_t)r * dbg_stride : nullptr,
+                        warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
   }
 }
 
 extern "C" int mpc_emu_solve(const float* rec, int n, int horizon, const float* rp, const int* rt,
                              const mpc::SolveParams* prm, float* grf0, float* grf_full,
-                             int32_t* status, double* info, double* dbg) {
-  if (horizon == 10) run<10>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, dbg);
-  else if (horizon == 16) run<16>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, dbg);
+                             int32_t* status, double* info, double* dbg, double* warm) {
+  if (horizon == 10) run<10>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, dbg, warm);
+  else if (horizon == 16) run<16>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, dbg, warm);
   else return -1;
   return 0;
 }
@@ -41,7 +42,7 @@ extern "C" int mpc_emu_solve(const float* rec, int n, int horizon, const float* 
 extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParams* tp, const float* dof,
                             const float* body, const float* est, const float* cmd, int has_weights, const int* gait,
                             const float* rp, const float* geom, const int* rt, int n, float* state,
-                            float* torques, float* grf0, float* records, int32_t* solved) {
+                            float* torques, float* grf0, float* records, int32_t* solved, double* warm) {
   constexpr int H = 10;
   using D = mpc::Dims<H>;
   mpc::SolveParams prm = *prm_in;
@@ -67,7 +68,7 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     if (do_solve) {
       mpc::fill_tables<H>(sm.data(), prm.dt);
       mpc::solve_robot<H>(rec, rp + (size_t)type * MPC_ROBOT_PARAMS_STRIDE, prm, sm.data(), grf, nullptr, &st_code,
-                          nullptr, nullptr, nullptr);
+                          nullptr, nullptr, nullptr, warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
       if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
     }
     mpc::tick_post(e, g, do_solve ? grf : nullptr, st, legs, torques + (size_t)r * 12);
