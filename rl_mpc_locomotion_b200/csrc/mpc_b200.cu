@@ -79,7 +79,7 @@ struct KernelCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 16;
 };
 
-template <int H>
+template <int H, bool WARM>
 __global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
 mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                  const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
@@ -109,7 +109,7 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
   mbar_wait(bar, 0);
 
   constexpr int dbg_stride = 12 * H + 144 * H * H + 12 * H + 20 * H + 1;
-  mpc::solve_robot<H>(rec_s, rp_s, prm, sm, grf0 + (size_t)robot * 12,
+  mpc::solve_robot<H, WARM>(rec_s, rp_s, prm, sm, grf0 + (size_t)robot * 12,
                       grf_full ? grf_full + (size_t)robot * 12 * H : nullptr,
                       status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
                       info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr,
@@ -130,7 +130,7 @@ struct TickCfg {
   static constexpr int SMEM_BYTES = OFF_IN + (24 + 18 + 16 + 24 + 12 + 2) * 4;
 };
 
-template <int H>
+template <int H, bool WARM>
 __global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
 mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const float* __restrict__ dof,
                 const float* __restrict__ body, const float* __restrict__ est, const float* __restrict__ cmd,
@@ -178,8 +178,8 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) records[(size_t)robot * K::REC_FLOATS + i] = rec_s[i];
   if (do_solve) {
     mpc::fill_tables<H>(sm, prm.dt, lane);
-    mpc::solve_robot<H>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, nullptr, nullptr,
-                        warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
+    mpc::solve_robot<H, WARM>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, nullptr, nullptr,
+                              warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
     __syncthreads();
     if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
   }
@@ -197,12 +197,18 @@ int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const fl
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mpc_tick_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(mpc_tick_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(mpc_tick_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem, tick)");
   if (n <= 0) return MPC_B200_OK;
-  mpc_tick_kernel<H><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp, geom, rt, n,
-                                                         state, torques, grf0, records, solved, warm);
+  if (warm)
+    mpc_tick_kernel<H, true><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp,
+                                                                  geom, rt, n, state, torques, grf0, records, solved, warm);
+  else
+    mpc_tick_kernel<H, false><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp,
+                                                                   geom, rt, n, state, torques, grf0, records, solved, nullptr);
   CK(cudaGetLastError());
   return MPC_B200_OK;
 }
@@ -261,13 +267,20 @@ int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     K::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      K::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
   if (n <= 0) return MPC_B200_OK;
-  mpc_solve_kernel<H><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status, resid,
-                                                           info, dbg, warm);
+  if (warm)
+    mpc_solve_kernel<H, true><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status,
+                                                                   resid, info, dbg, warm);
+  else
+    mpc_solve_kernel<H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status,
+                                                                    resid, info, dbg, nullptr);
   CK(cudaGetLastError());
   return MPC_B200_OK;
 }
@@ -347,8 +360,8 @@ int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int*
   if (regs_per_thread) {
     *regs_per_thread = -1;
     cudaFuncAttributes a;
-    cudaError_t e = horizon == 10 ? cudaFuncGetAttributes(&a, mpc_solve_kernel<10>)
-                                  : cudaFuncGetAttributes(&a, mpc_solve_kernel<16>);
+    cudaError_t e = horizon == 10 ? cudaFuncGetAttributes(&a, mpc_solve_kernel<10, false>)
+                                  : cudaFuncGetAttributes(&a, mpc_solve_kernel<16, false>);
     if (e == cudaSuccess) *regs_per_thread = a.numRegs;
     else cudaGetLastError();
   }

@@ -209,7 +209,7 @@ MPC_FN void fill_tables(double* sm, double dt
   WSYNC();
 }
 
-template <int H>
+template <int H, bool WARM = false>
 MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& prm, double* sm,
                         float* grf0, float* grf_full, int32_t* status_out, float* resid_out,
                         double* info_out, double* dbg_out, double* warm
@@ -224,7 +224,9 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   // they are when the data is re-scaled, exactly as osqp_update_P_A does) and the previous
   // UNSCALED q[12h] (osqp_update_P_A re-runs scale_data before osqp_update_lin_cost installs the
   // new q, so the cost normalisation c sees the OLD q).
-  const bool warm_valid = warm != nullptr && warm[0] != 0.0;
+  // WARM is a compile-time switch so that the cold-start kernel carries none of this code.
+  bool warm_valid = false;
+  if constexpr (WARM) warm_valid = warm != nullptr && warm[0] != 0.0;
   constexpr int NS = D::NSLOT, NW = D::NW, NV = D::NV, NRS = D::NRS;
   double* const Wp = sm + D::OFF_WP;
   double* const vecA = sm + D::OFF_VECA;
@@ -266,7 +268,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   PER_LANE_ARR(double, zv, [NS][5]);
   PER_LANE_ARR(double, yv, [NS][5]);
   PER_LANE_ARR(double, qb, [NS][3]);   // scaled linear cost
-  PER_LANE_ARR(double, qnew, [NS][3]); // unscaled linear cost of THIS problem
   PER_LANE_ARR(double, Dv, [NS][3]);   // Ruiz D
   PER_LANE_ARR(double, Ev, [NS][5]);   // Ruiz E
   PER_LANE_ARR(double, di, [NS][6]);   // Delta^-1 (sym 3x3)
@@ -458,9 +459,16 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       double q = 0;
 #pragma unroll
       for (int c = 0; c < 6; ++c) q += _(wbl)[c][a] * vt[6 * k + c];
-      _(qb)[s][a] = _(valid)[s] ? 2.0 * q : 0.0;
-      _(qnew)[s][a] = _(qb)[s][a];
-      if (warm_valid && _(valid)[s]) _(qb)[s][a] = warm[2 + 52 * H + 3 * j + a];   // scale with the OLD q
+      const double qn = _(valid)[s] ? 2.0 * q : 0.0;
+      _(qb)[s][a] = qn;
+      if (dbg_out && _(valid)[s]) dbg_out[3 * j + a] = qn;   // unscaled q for builder tests
+      if constexpr (WARM) {
+        if (warm && _(valid)[s]) {
+          // the workspace keeps the UNSCALED q; scale_data below must see the OLD one (if any)
+          if (warm_valid) _(qb)[s][a] = warm[2 + 52 * H + 3 * j + a];
+          warm[2 + 52 * H + 3 * j + a] = qn;
+        }
+      }
       _(Dv)[s][a] = 1.0;
       _(xv)[s][a] = 0.0;
     }
@@ -474,16 +482,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   for (int v = lane; v < NV; v += NL) Dsm[v] = 1.0;
   LANES_END
   WSYNC();
-  if (dbg_out) {  // unscaled q for builder tests
-    LANES_BEGIN
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if (_(valid)[s])
-#pragma unroll
-        for (int a = 0; a < 3; ++a) dbg_out[3 * (lane + NL * s) + a] = _(qnew)[s][a];
-    LANES_END
-  }
-
   // ------------------------------------------------------------------ S2: Ruiz scaling
   // G1 = Wb'^T Q1' Wb', G2 = Wb'^T Q2' Wb' (12x12) staged in the (still unused) triangle buffer.
   double* const G1 = Wp;
@@ -991,7 +989,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 
   // ------------------------------------------------------------------ S3: rho, factor
   double rho = fmin(fmax(prm.rho0, kRhoMin), kRhoMax);  // auxil.c:82
-  if (warm_valid) {
+  if constexpr (WARM) if (warm_valid) {
     rho = warm[1];   // settings->rho keeps the value adapted during the previous solve
     LANES_BEGIN
 #pragma unroll
@@ -1001,7 +999,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           // osqp_update_lin_cost: q = c * (D .* q_new)   (osqp.c:752-782)
-          _(qb)[s][a] = (_(Dv)[s][a] * _(qnew)[s][a]) * cscale;
+          _(qb)[s][a] = (_(Dv)[s][a] * warm[2 + 52 * H + 3 * j + a]) * cscale;
           _(xv)[s][a] = warm[2 + 3 * j + a];
         }
 #pragma unroll
@@ -1394,31 +1392,36 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       // polish vectors: Dsm is free here (D is also held in registers), colb holds xi_0
       double* const pv = Dsm;        // [nf] right-hand side / solution of the triangular solves
       double* const pxi = Dsm + NW;  // [nf] current xi
-      double* const pxi0 = colb;     // [nf] first regularised solve
-      auto tri_solve = [&]() {  // pv <- (L L^T)^-1 pv
-        for (int j = 0; j < nf; ++j) {
-          LANES_BEGIN
-          const double yj = pv[j] * dinv[j];
-          for (int i = j + 1 + lane; i < nf; i += NL) pv[i] -= Wp[tri(i) + j] * yj;
-          LANES_END
-          WSYNC();
-          LANES_BEGIN
-          if (lane == 0) pv[j] = pv[j] * dinv[j];
-          LANES_END
-          WSYNC();
+      double* const pxi0 = colb;     // [nf] first regularised solve (colb is free again after invert_lower)
+      invert_lower(nf);             // W = L^-1: every solve below is two barrier-light mat-vecs
+      auto tri_solve = [&]() {      // pv <- W^T (W pv) = (L L^T)^-1 pv
+        double* const ty = colb + NW;
+        LANES_BEGIN
+        for (int i = lane; i < nf; i += NL) {
+          const double* rowi = Wp + tri(i);
+          double a0 = dinv[i] * pv[i], a1 = 0.0;
+          int k = 0;
+          for (; k + 1 < i; k += 2) {
+            a0 += rowi[k] * pv[k];
+            a1 += rowi[k + 1] * pv[k + 1];
+          }
+          if (k < i) a0 += rowi[k] * pv[k];
+          ty[i] = a0 + a1;
         }
-        for (int j = nf - 1; j >= 0; --j) {
-          LANES_BEGIN
-          const double xj = pv[j] * dinv[j];
-          const double* rowj = Wp + tri(j);
-          for (int i = lane; i < j; i += NL) pv[i] -= rowj[i] * xj;
-          LANES_END
-          WSYNC();
-          LANES_BEGIN
-          if (lane == 0) pv[j] = pv[j] * dinv[j];
-          LANES_END
-          WSYNC();
+        LANES_END
+        WSYNC();
+        LANES_BEGIN
+        for (int c = lane; c < nf; c += NL) {
+          double a0 = dinv[c] * ty[c];
+          const double* p = Wp + tri(c + 1) + c;
+          for (int i = c + 1; i < nf; ++i) {
+            a0 += p[0] * ty[i];
+            p += i + 1;
+          }
+          pv[c] = a0;
         }
+        LANES_END
+        WSYNC();
       };
       // first solve: (K_f + delta) xi_0 = b
       LANES_BEGIN
@@ -1587,16 +1590,13 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
     }
   }
-  if (warm) {   // leave the workspace state for the next solve (scaled iterates, rho, unscaled q)
+  if constexpr (WARM) if (warm) {   // leave the workspace state for the next solve (scaled iterates, rho)
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s]) {
         const int j = lane + NL * s;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          warm[2 + 3 * j + a] = _(xv)[s][a];
-          warm[2 + 52 * H + 3 * j + a] = _(qnew)[s][a];
-        }
+        for (int a = 0; a < 3; ++a) warm[2 + 3 * j + a] = _(xv)[s][a];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
           warm[2 + 12 * H + 5 * j + r] = _(zv)[s][r];

@@ -21,7 +21,7 @@ static void run(const float* rec, int n, const float* rp, const int* rt, const m
   const int dbg_stride = D::NV + D::NV * D::NV + D::NV + 20 * H + 1;
   for (int r = 0; r < n; ++r) {
     const float* rpr = rp + (size_t)(rt ? rt[r] : 0) * MPC_ROBOT_PARAMS_STRIDE;
-    mpc::solve_robot<H>(rec + (size_t)r * stride, rpr, prm, sm.data(), grf0 + (size_t)r * 12,
+    mpc::solve_robot<H, true>(rec + (size_t)r * stride, rpr, prm, sm.data(), grf0 + (size_t)r * 12,
                         grf_full ? grf_full + (size_t)r * 12 * H : nullptr, status ? status + r : nullptr,
                         nullptr, info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr,
                         dbg ? dbg + (size_t)r * dbg_stride : nullptr,
@@ -67,7 +67,7 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     if (records) std::memcpy(records + (size_t)r * stride, rec, sizeof(rec));
     if (do_solve) {
       mpc::fill_tables<H>(sm.data(), prm.dt);
-      mpc::solve_robot<H>(rec, rp + (size_t)type * MPC_ROBOT_PARAMS_STRIDE, prm, sm.data(), grf, nullptr, &st_code,
+      mpc::solve_robot<H, true>(rec, rp + (size_t)type * MPC_ROBOT_PARAMS_STRIDE, prm, sm.data(), grf, nullptr, &st_code,
                           nullptr, nullptr, nullptr, warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
       if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
     }
