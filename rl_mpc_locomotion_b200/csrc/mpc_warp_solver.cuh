@@ -89,7 +89,8 @@ struct Dims {
   static constexpr int OFF_NN = OFF_GAM + H * H;         // [H][H]
   static constexpr int OFF_WB = OFF_NN + H * H;          // [6][12] balanced wrench map
   static constexpr int OFF_Q1S = OFF_WB + 72;            // [6][6] Q1'
-  static constexpr int OFF_DSM = OFF_Q1S + 36;           // [NV] D (scaling) for broadcast reads
+  static constexpr int OFF_Q2S = OFF_Q1S + 36;           // [6] diag of Q2' (+2 pad)
+  static constexpr int OFF_DSM = OFF_Q2S + 8;            // [NV] D (scaling) for broadcast reads
   static constexpr int SMEM_DOUBLES = OFF_DSM + NV;
   static_assert(12 * NW + NW / 2 + 8 <= SCR_SIZE, "polish scratch does not fit");
   static_assert(NLS * 21 <= NTRI && 288 + 72 <= NTRI, "staging does not fit in the triangle buffer");
@@ -238,6 +239,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   double* const dinv = sm + D::OFF_DINV;
   double* const colb = sm + D::OFF_COL;
   double* const q1s = sm + D::OFF_Q1S;
+  double* const q2s = sm + D::OFF_Q2S;
   const double* const gam = sm + D::OFF_GAM;
   const double* const nnm = sm + D::OFF_NN;
   double* const Wb = sm + D::OFF_WB;
@@ -458,7 +460,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     for (int a = 0; a < 3; ++a) {
       double q = 0;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) q += _(wbl)[c][a] * vt[6 * k + c];
+      for (int c = 0; c < 6; ++c) q += Wb[c * 12 + 3 * (lane & 3) + a] * vt[6 * k + c];
       const double qn = _(valid)[s] ? 2.0 * q : 0.0;
       _(qb)[s][a] = qn;
       if (dbg_out && _(valid)[s]) dbg_out[3 * j + a] = qn;   // unscaled q for builder tests
@@ -489,6 +491,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   double* const Y1 = Wp + 288;  // Q1' Wb' (6x12)
   LANES_BEGIN
   for (int e = lane; e < 36; e += NL) q1s[e] = Q1at(e / 6, e % 6);
+  if (lane < 6) q2s[lane] = q2d[lane];
   for (int e = lane; e < 72; e += NL) {
     const int c = e / 12, b = e % 12;
     double y1 = 0;
@@ -749,7 +752,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
 #pragma unroll
-          for (int a = 0; a < 3; ++a) X[c][a] = _(wbl)[c][a] * Dd[a];
+          for (int a = 0; a < 3; ++a) X[c][a] = Wb[c * 12 + 3 * (lane & 3) + a] * Dd[a];
           mul3sym(_(di)[s], X[c], Y[c]);
         }
         int e = 0;
@@ -793,7 +796,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       double* const row = Wp + tri(i);
       const double* q1r = q1s + c * 6;
       for (int k2 = 0; k2 <= k; ++k2) {
-        const double g2 = 2.0 * cscale * gam[k * H + k2], n2 = 2.0 * cscale * nnm[k * H + k2] * q2d[c];
+        const double g2 = 2.0 * cscale * gam[k * H + k2], n2 = 2.0 * cscale * nnm[k * H + k2] * q2s[c];
         const int cend = (k2 == k) ? c : 5;
         for (int c2 = 0; c2 <= cend; ++c2) {
           double v = g2 * q1r[c2] + (c == c2 ? n2 : 0.0);
@@ -914,7 +917,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int a = 0; a < 3; ++a) {
           double t = 0;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) t += _(wbl)[c][a] * vecB[6 * k + c];
+          for (int c = 0; c < 6; ++c) t += Wb[c * 12 + 3 * (lane & 3) + a] * vecB[6 * k + c];
           u[a] = _(Dv)[s][a] * t;
         }
         mul3sym(_(di)[s], u, du);
@@ -953,9 +956,9 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       const int k = i / 6, c = i % 6;
       double a1 = 0;
 #pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2) a1 += Q1at(c, c2) * vt[6 * k + c2];
+      for (int c2 = 0; c2 < 6; ++c2) a1 += q1s[c * 6 + c2] * vt[6 * k + c2];
       vg[i] = a1;
-      vw[i] = q2d[c] * vt[i];
+      vw[i] = q2s[c] * vt[i];
     }
     LANES_END
     WSYNC();
@@ -978,7 +981,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int a = 0; a < 3; ++a) {
           double t = 0;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) t += _(wbl)[c][a] * vecB[6 * k + c];
+          for (int c = 0; c < 6; ++c) t += Wb[c * 12 + 3 * (lane & 3) + a] * vecB[6 * k + c];
           const double d = _(Dv)[s][a];
           _(xt)[s][a] = cscale * alpha * d * d * _(tmp3)[s][a] + d * t;
         }
@@ -1329,14 +1332,14 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
             for (int c = 0; c < 6; ++c) {
               m[c] = 0;
 #pragma unroll
-              for (int a = 0; a < 3; ++a) m[c] += _(wbl)[c][a] * _(Dv)[s][a] * nu[a];
+              for (int a = 0; a < 3; ++a) m[c] += Wb[c * 12 + 3 * (lane & 3) + a] * _(Dv)[s][a] * nu[a];
               Mf[6 * f + c] = m[c];
             }
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
               double a1 = 0;
 #pragma unroll
-              for (int c2 = 0; c2 < 6; ++c2) a1 += Q1at(c, c2) * m[c2];
+              for (int c2 = 0; c2 < 6; ++c2) a1 += q1s[c * 6 + c2] * m[c2];
               A1f[6 * f + c] = a1;
             }
             kf[f] = k;
@@ -1359,7 +1362,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
             d1 += m[c] * A1f[6 * f2 + c];
-            d2 += m[c] * q2d[c] * Mf[6 * f2 + c];
+            d2 += m[c] * q2s[c] * Mf[6 * f2 + c];
           }
           const double v = 2.0 * cscale * (gam[k * H + k2] * d1 + nnm[k * H + k2] * d2);
           if (f2 == f) dinv[f] = v + prm.delta;
