@@ -201,6 +201,8 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
 #define MPC_ST_CPHASE     71   /* [4]  estimator contact phase                  */
 #define MPC_ST_HIST       75   /* [4][3] foot contact history                   */
 #define MPC_ST_NORMAL     87   /* [3]  ground normal (yaw frame)                */
+#define MPC_ST_UNSAFE     90   /* int  locomotionSafe() == False this tick (FSM_State_Locomotion.py:104-136);
+                                        only evaluated when d_body is given                */
 #define MPC_TICK_STATE_STRIDE 96
 
 typedef struct MpcB200TickParams {

@@ -169,11 +169,17 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
   for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) rec_s[i] = 0.0f;
   __syncthreads();
   if (!est) {  // StateEstimator.update on the device (uses the previous tick's ground normal)
-    if (lane == 0) mpc::estimator_update(body + (size_t)robot * 13, st_s + MPC_ST_NORMAL, est_s);
+    if (lane == 0) mpc::estimator_update(body + (size_t)robot * 13, st_s + MPC_ST_NORMAL, est_s, grf_s);
     __syncthreads();
   }
+  const bool have_rp = !est;   // grf_s[0..1] temporarily holds the world roll / pitch (float16 values)
+  const float roll16 = have_rp ? grf_s[0] : 0.0f, pitch16 = have_rp ? grf_s[1] : 0.0f;
   const int g = gait ? gait[robot] : 0;
   const int do_solve = mpc::tick_pre<H>(dof_s, est_s, cmd_s, has_weights, g, geom_s, tp, st_s, rec_s, legs_s, lane);
+  if (have_rp && lane == 0) {
+    const float rp2[2] = {roll16, pitch16};
+    reinterpret_cast<int*>(st_s)[MPC_ST_UNSAFE] = mpc::locomotion_unsafe(rp2, legs_s + mpc::LG_P, mpc::LG_STRIDE);
+  }
   if (records)
     for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) records[(size_t)robot * K::REC_FLOATS + i] = rec_s[i];
   if (do_solve) {

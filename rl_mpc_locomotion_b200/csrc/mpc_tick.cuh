@@ -97,7 +97,7 @@ MPC_LANEFN void mm3_f16(const float* a, const float* b, float* o) {   // o = h16
 }
 // quat_to_rpy on a quaternion whose w is a Python float and x, y, z are float16 scalars
 // (what rot_to_quat returns for tr > 0, orientation_tools.py:120-133, 162-175)
-MPC_LANEFN void estimator_update(const float* body, const float* normal, float* est) {
+MPC_LANEFN void estimator_update(const float* body, const float* normal, float* est, float* rp16 = nullptr) {
   const float qx = body[3], qy = body[4], qz = body[5], qw = body[6];
   // quat_to_rot (orientation_tools.py:135-151): float32 expressions, stored as float16, transposed
   const float e0 = qw, e1 = qx, e2 = qy, e3 = qz;
@@ -111,6 +111,11 @@ MPC_LANEFN void estimator_update(const float* body, const float* normal, float* 
   for (int r = 0; r < 3; ++r) {   // vBody = rBody @ vWorld, omegaBody = rBody @ omegaWorld (float32)
     est[MPC_EST_VBODY + r] = rB[3 * r] * body[7] + rB[3 * r + 1] * body[8] + rB[3 * r + 2] * body[9];
     est[MPC_EST_OMEGABODY + r] = rB[3 * r] * body[10] + rB[3 * r + 1] * body[11] + rB[3 * r + 2] * body[12];
+  }
+  if (rp16) {  // world-frame roll / pitch of quat_to_rpy (float16), used by locomotionSafe()
+    rp16[0] = h16(atan2f(2.0f * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz));
+    const double as0 = (double)(-2.0f * (qx * qz - qw * qy));
+    rp16[1] = round_f16(asin(as0 < 0.99999 ? as0 : 0.99999));
   }
   // yaw of quat_to_rpy(orientation) (float32 args, float16 store)
   const float yaw16 = h16(atan2f(2.0f * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz));
@@ -162,6 +167,19 @@ MPC_LANEFN void estimator_update(const float* body, const float* normal, float* 
   est[MPC_EST_RPYBODY + 0] = h16(atan2f(num0, den0));
   est[MPC_EST_RPYBODY + 1] = round_f16(asin(as_));
   est[MPC_EST_RPYBODY + 2] = h16(atan2f(num2, den2));
+}
+
+// FSM_State_Locomotion.locomotionSafe (FSM_states/FSM_State_Locomotion.py:104-136), including its
+// `fabs(bool)` slips: only POSITIVE roll beyond 40 deg and only leg y > 0.18 trip.
+MPC_LANEFN int locomotion_unsafe(const float* rp16, const float* legs_p /* 4 x stride */, int stride) {
+  const float lim = (float)(40.0 * 3.14159265358979323846 / 180.0);
+  if (rp16[0] > lim) return 1;
+  if (fabsf(rp16[1]) > lim) return 1;
+  for (int l = 0; l < 4; ++l) {
+    if (legs_p[l * stride + 2] > 0.0f) return 1;
+    if (legs_p[l * stride + 1] > 0.18f) return 1;
+  }
+  return 0;
 }
 
 // per-leg scratch in shared memory (floats)

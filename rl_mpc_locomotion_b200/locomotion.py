@@ -49,6 +49,13 @@ class BatchedLocomotion:
         # (cold start = the golden-vector semantics)
         self.warm = torch.zeros((self.n, 2 + 64 * horizon), dtype=torch.float64, device=dev) if warm_start else None
 
+    @property
+    def unsafe(self) -> torch.Tensor:
+        """Per-robot ``not locomotionSafe()`` of the last tick (FSM_State_Locomotion.py:104-136):
+        the host FSM shell uses it to hand a robot over to RecoveryStand, as the reference does
+        (FSM_State_Locomotion.py:62-81).  Evaluated only when ``root_states`` are passed to run()."""
+        return self.state.view(torch.int32)[:, 90] != 0
+
     def reset(self, idx=None):
         """``controller.reset()`` for the given robots (aliengo.py:333-334); all when None.
         ``ConvexMPCLocomotion.initialize`` builds a new ``ConvexMpc`` (ConvexMPCLocomotion.py:102),

@@ -86,3 +86,22 @@ def test_tick_replay_with_warm_started_osqp_workspace():
     w = replay("aliengo_trot_warm", _emu_tick, device_estimator=True, warm=warm)
     print(w)
     assert w["rec"] < 5e-6 and w["fff"] < 5e-3 and w["tau"] < 2e-3
+
+
+def test_locomotion_safe_flag_replicates_reference_quirks():
+    """locomotionSafe (FSM_State_Locomotion.py:104-136): roll > 40 deg trips, roll < -40 deg does
+    NOT (`fabs(bool)`), |pitch| > 40 deg trips, a foot above the hip trips."""
+    def quat(roll, pitch):
+        cr, sr, cp, sp = np.cos(roll / 2), np.sin(roll / 2), np.cos(pitch / 2), np.sin(pitch / 2)
+        return [sr * cp, cr * sp, -sr * sp, cr * cp]      # yaw = 0, xyzw
+    stand = np.tile([0.0, 0.8, -1.6], 4)
+    up = stand.copy(); up[1:3] = [3.0, -0.2]               # leg 0 folded above the hip
+    cases = [(0.0, 0.0, stand, 0), (0.8, 0.0, stand, 1), (-0.8, 0.0, stand, 0), (0.0, 0.8, stand, 1),
+             (0.0, -0.8, stand, 1), (0.0, 0.0, up, 1)]
+    for roll, pitch, q, expect in cases:
+        state = initial_tick_state([0])
+        body = np.array([[0, 0, 0.35] + quat(roll, pitch) + [0.3, 0, 0, 0, 0, 0]], np.float32)
+        dof = np.stack([q, np.zeros(12)], 1)[None].astype(np.float32)
+        cmd = np.zeros((1, 16), np.float32)
+        emu.tick(state, dof, None, cmd, 0, [0], params_table(), geom_table(), [0], body=body)
+        assert int(state.view(np.int32)[0, 90]) == expect, (roll, pitch, expect)

@@ -61,9 +61,11 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     const float* g = geom + (size_t)type * MPC_GEOM_STRIDE;
     float est_local[MPC_EST_STRIDE];
     const float* e = est ? est + (size_t)r * MPC_EST_STRIDE : est_local;
-    if (!est) mpc::estimator_update(body + (size_t)r * 13, st + MPC_ST_NORMAL, est_local);
+    float rp16[2] = {0, 0};
+    if (!est) mpc::estimator_update(body + (size_t)r * 13, st + MPC_ST_NORMAL, est_local, rp16);
     const int do_solve = mpc::tick_pre<H>(dof + (size_t)r * 24, e, cmd + (size_t)r * MPC_CMD_STRIDE, has_weights,
                                           gait ? gait[r] : 0, g, *tp, st, rec, legs);
+    if (!est) reinterpret_cast<int*>(st)[MPC_ST_UNSAFE] = mpc::locomotion_unsafe(rp16, legs + mpc::LG_P, mpc::LG_STRIDE);
     if (records) std::memcpy(records + (size_t)r * stride, rec, sizeof(rec));
     if (do_solve) {
       mpc::fill_tables<H>(sm.data(), prm.dt);
