@@ -25,7 +25,7 @@
 // is two conflict-free triangular mat-vecs out of shared memory (no dependent chain).
 //
 // Written in the warp-program dialect of warp_prog.h: compiles for sm_100a (product) and,
-// with -DMPC_EMULATE, as a sequential 32-lane emulation for GPU-less CI.
+// with -DMPC_EMULATE, as a sequential lane-by-lane emulation for GPU-less CI.
 #pragma once
 
 #include <math.h>
@@ -70,8 +70,6 @@ struct Dims {
   static constexpr int NW = 6 * H;              // wrench-space dimension
   static constexpr int NWS = (NW + NL - 1) / NL;
   static constexpr int NVS = (NV + NL - 1) / NL;
-  static constexpr int NP = (NW + 1) / 2;             // row pairs (i, NW-1-i) of the triangle
-  static constexpr int NRS = 2 * ((NP + NL - 1) / NL);  // (unused) triangle rows per lane
   static constexpr int NTRI = NW * (NW + 1) / 2;      // packed lower triangle (row i at i(i+1)/2; slot i of row i unused)
   // shared-memory layout (doubles)
   static constexpr int OFF_WP = 0;                       // [NTRI] Hm -> L -> W = L^-1, row-packed
@@ -102,18 +100,6 @@ struct Dims {
 // different 8-byte bank pairs at the same column (row walks are conflict-free) and a fixed row
 // is contiguous in k (column walks across lanes touch consecutive words).
 MPC_LANEFN int tri(int i) { return (i * (i + 1)) >> 1; }
-// Rows of an n x n triangle owned by `lane`: rows are paired (p, n-1-p) so that every lane
-// carries the same number of elements (n-1) per pair.
-MPC_LANEFN int rowmap(int lane, int n, int r) {
-  const int p = lane + NL * (r >> 1);
-  if (p >= ((n + 1) >> 1)) return -1;
-  if (r & 1) {
-    const int q = n - 1 - p;
-    return q > p ? q : -1;
-  }
-  return p;
-}
-
 // ----------------------------------------------------------------- lane-local helpers
 MPC_LANEFN double limit_scaling(double v) {  // scaling.c:7-14
   v = v < kMinScaling ? 1.0 : v;
@@ -228,7 +214,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   // WARM is a compile-time switch so that the cold-start kernel carries none of this code.
   bool warm_valid = false;
   if constexpr (WARM) warm_valid = warm != nullptr && warm[0] != 0.0;
-  constexpr int NS = D::NSLOT, NW = D::NW, NV = D::NV, NRS = D::NRS;
+  constexpr int NS = D::NSLOT, NW = D::NW, NV = D::NV;
   double* const Wp = sm + D::OFF_WP;
   double* const vecA = sm + D::OFF_VECA;
   double* const vecB = sm + D::OFF_VECB;
@@ -566,7 +552,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   for (int it = 0; it < prm.scaling_iters; ++it) {
     // D_temp, E_temp from the current scaled P, A (scaling.c:78-93)
     LANES_BEGIN
-    double qmax = 0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       const int j = lane + NL * s;
@@ -663,32 +648,38 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   };
 
   // dense Cholesky (left-looking) of the leading n x n block held as: strictly-lower triangle in
-  // Wp (row-packed), diagonal in dinv[].  On exit Wp holds L (strictly lower) and dinv[i] = 1/L_ii.
+  // Wp (row-packed), diagonal in colb[0..n).  On exit Wp holds L (strictly lower), dinv[i] = 1/L_ii.
   // Row i is owned by lane i % NL; inner loops have warp-uniform trip counts (j).
   auto cholesky = [&](int n) {
+    // ONE barrier per column: every lane that owns a row below the diagonal recomputes the pivot
+    // d_j = H_jj - sum_k L_jk^2 from the row-j values it loads anyway, so it can scale its own
+    // element without waiting for the owner of row j.  The input diagonal lives in hdiag (= colb,
+    // free until invert_lower) so that writing dinv[j] cannot race with readers of H_jj.
+    double* const hdiag = colb;
     for (int j = 0; j < n; ++j) {
       const double* rowj = Wp + tri(j);
       LANES_BEGIN
-      // first owned row >= j
       for (int i = j + ((lane - j) & (NL - 1)); i < n; i += NL) {
         double* rowi = Wp + tri(i);
-        double a0 = (i == j) ? dinv[j] : rowi[j], a1 = 0.0;
+        double a0 = (i == j) ? 0.0 : rowi[j], a1 = 0.0, d0 = hdiag[j], d1 = 0.0;
         int k = 0;
 #pragma unroll 2
         for (; k + 1 < j; k += 2) {
-          a0 -= rowi[k] * rowj[k];
-          a1 -= rowi[k + 1] * rowj[k + 1];
+          const double l0 = rowj[k], l1 = rowj[k + 1];
+          a0 -= rowi[k] * l0;
+          a1 -= rowi[k + 1] * l1;
+          d0 -= l0 * l0;
+          d1 -= l1 * l1;
         }
-        if (k < j) a0 -= rowi[k] * rowj[k];
-        a0 += a1;
-        if (i == j) dinv[j] = 1.0 / sqrt(a0);
-        else rowi[j] = a0;                       // unscaled; scaled after the barrier
+        if (k < j) {
+          const double l0 = rowj[k];
+          a0 -= rowi[k] * l0;
+          d0 -= l0 * l0;
+        }
+        const double inv = 1.0 / sqrt(d0 + d1);
+        if (i == j) dinv[j] = inv;
+        else rowi[j] = (a0 + a1) * inv;
       }
-      LANES_END
-      WSYNC();
-      LANES_BEGIN
-      const double inv = dinv[j];
-      for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) Wp[tri(i) + j] *= inv;
       LANES_END
       WSYNC();
     }
@@ -803,7 +794,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
           if (k == k2) v += Finv[k * 36 + c * 6 + c2];
           const int i2 = 6 * k2 + c2;
           if (i2 < i) row[i2] = v;
-          else dinv[i] = v;
+          else colb[i] = v;      // input diagonal for cholesky() (hdiag)
         }
       }
     }
@@ -1365,7 +1356,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
             d2 += m[c] * q2s[c] * Mf[6 * f2 + c];
           }
           const double v = 2.0 * cscale * (gam[k * H + k2] * d1 + nnm[k * H + k2] * d2);
-          if (f2 == f) dinv[f] = v + prm.delta;
+          if (f2 == f) colb[f] = v + prm.delta;   // hdiag of cholesky()
           else row[f2] = v;
         }
       }
@@ -1384,7 +1375,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
               for (int a = 0; a < 3; ++a)
                 v += _(Yb)[s][p][a] * cscale * alpha * _(Dv)[s][a] * _(Dv)[s][a] * _(Yb)[s][p2][a];
               const int f = f0 + (p - _(rk)[s]), f2 = f0 + (p2 - _(rk)[s]);
-              if (f == f2) dinv[f] += v;
+              if (f == f2) colb[f] += v;
               else Wp[tri(f) + f2] += v;
             }
         }
