@@ -52,8 +52,8 @@ extern "C" {
 #define MPC_B200_MAX_HORIZON 16
 
 /* per-robot OSQP workspace state carried between consecutive solves (float64):
- * valid flag, rho, x[12h], z[20h], y[20h] (scaled iterates), previous unscaled q[12h]        */
-#define MPC_WARM_STRIDE(h)  (2 + 64 * (h))
+ * flag, rho, x[12h], z[20h], y[20h] (scaled iterates), two slots of unscaled q[12h]            */
+#define MPC_WARM_STRIDE(h)  (2 + 76 * (h))
 
 /* error codes */
 #define MPC_B200_OK            0
@@ -66,6 +66,9 @@ extern "C" {
 #define MPC_STATUS_SOLVED          1   /* mirrors OSQP_SOLVED (constants.h)   */
 #define MPC_STATUS_MAX_ITER       -2   /* mirrors OSQP_MAX_ITER_REACHED       */
 #define MPC_STATUS_NON_FINITE     -7   /* NaN/Inf met -> forces zeroed        */
+#define MPC_STATUS_POLISH_OVERFLOW -90 /* internal: more free coordinates than the fast kernel's polish
+                                          buffer (> 2h stance leg-steps); re-solved by the overflow kernel
+                                          inside the same mpc_b200_solve_batch call, never returned    */
 
 /* Solver modes */
 #define MPC_MODE_OSQP   0  /* reproduce the reference's OSQP run step for step (fp64): Ruiz

@@ -40,7 +40,7 @@ class BatchedConvexMpc:
         """Fresh (all-cold) OSQP workspace-state tensor for `n` robots: pass it as ``warm=`` to
         consecutive solves of the same robots to get the reference's ``warm_start`` behaviour
         (mpc_osqp.cc:708, :760-778); zero a row to force ``osqp_setup`` semantics for that robot."""
-        return torch.zeros((n, 2 + 64 * self.horizon), dtype=torch.float64, device=self.device)
+        return torch.zeros((n, 2 + 76 * self.horizon), dtype=torch.float64, device=self.device)
 
     def solve(self, records: torch.Tensor, robot_type: torch.Tensor | None = None, *, full: bool = False,
               status: bool = True, info: bool = False, out: torch.Tensor | None = None,
@@ -66,7 +66,7 @@ class BatchedConvexMpc:
             assert robot_type.is_cuda and robot_type.dtype == torch.int32 and robot_type.shape == (n,)
         if warm is not None:
             assert warm.is_cuda and warm.dtype == torch.float64 and warm.is_contiguous()
-            assert tuple(warm.shape) == (n, 2 + 64 * self.horizon), warm.shape
+            assert tuple(warm.shape) == (n, 2 + 76 * self.horizon), warm.shape
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = _lib.lib().mpc_b200_solve_batch(C.byref(self.settings), ptr(records), ptr(self.robot_params),

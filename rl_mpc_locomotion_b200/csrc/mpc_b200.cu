@@ -67,9 +67,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #define MPC_MIN_CTAS 6   // resident robots per SM the register allocation is tuned for (168 regs: no hot-loop spills)
 #endif
 
-template <int H>
+template <int H, int PCAP = 6 * H>
 struct KernelCfg {
-  using D = mpc::Dims<H>;
+  using D = mpc::Dims<H, PCAP>;
   static constexpr int REC_FLOATS = MPC_REC_STRIDE(H);
   static constexpr int REC_BYTES = REC_FLOATS * 4;
   // [solver doubles][record floats (16B aligned)][robot params 12 floats][mbarrier]
@@ -79,14 +79,17 @@ struct KernelCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 16;
 };
 
-template <int H, bool WARM>
-__global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
+// PCAP = polish capacity (free coordinates).  The fast instantiation (6H) covers every contact
+// table with <= 2H stance leg-steps; robots beyond that leave MPC_STATUS_POLISH_OVERFLOW and are
+// re-solved by the ONLY_OVERFLOW instantiation (PCAP = 12H, larger shared-memory footprint).
+template <int H, bool WARM, int PCAP, bool ONLY_OVERFLOW>
+__global__ void __launch_bounds__(MPC_NL, (PCAP > 6 * H ? 1 : MPC_MIN_CTAS))
 mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                  const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
                  int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
                  int32_t* __restrict__ status, float* __restrict__ resid, double* __restrict__ info,
                  double* __restrict__ dbg, double* __restrict__ warm) {
-  using K = KernelCfg<H>;
+  using K = KernelCfg<H, PCAP>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   float* rec_s = reinterpret_cast<float*>(smem_raw + K::OFF_REC);
@@ -95,6 +98,9 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
   const int lane = threadIdx.x;
   const int robot = blockIdx.x;
   if (robot >= n_robots) return;
+  if constexpr (ONLY_OVERFLOW) {
+    if (status[robot] != MPC_STATUS_POLISH_OVERFLOW) return;   // uniform per CTA
+  }
 
   // stage the robot's state block with one TMA bulk copy while the tables are built
   if (lane == 0) {
@@ -104,12 +110,12 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
   }
   const int type = robot_type ? robot_type[robot] : 0;
   if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
-  mpc::fill_tables<H>(sm, prm.dt, lane);
+  mpc::fill_tables<H, PCAP>(sm, prm.dt, lane);
   WSYNC();
   mbar_wait(bar, 0);
 
   constexpr int dbg_stride = 12 * H + 144 * H * H + 12 * H + 20 * H + 1;
-  mpc::solve_robot<H, WARM>(rec_s, rp_s, prm, sm, grf0 + (size_t)robot * 12,
+  mpc::solve_robot<H, WARM, PCAP>(rec_s, rp_s, prm, sm, grf0 + (size_t)robot * 12,
                       grf_full ? grf_full + (size_t)robot * 12 * H : nullptr,
                       status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
                       info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr,
@@ -265,30 +271,44 @@ int check_settings(const MpcB200Settings* s) {
   return MPC_B200_OK;
 }
 
+template <int H, bool WARM>
+int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n, float* grf0,
+             float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
+             cudaStream_t stream) {
+  using K = KernelCfg<H>;
+  using KB = KernelCfg<H, 12 * H>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, WARM, 6 * H, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, WARM, 12 * H, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, KB::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
+  if (n <= 0) return MPC_B200_OK;
+  // the overflow pass needs the per-robot status even when the caller does not want it
+  int32_t* st = status;
+  if (!st) CK(cudaMallocAsync((void**)&st, (size_t)n * sizeof(int32_t), stream));
+  mpc_solve_kernel<H, WARM, 6 * H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, st,
+                                                                               resid, info, dbg, warm);
+  CK(cudaGetLastError());
+  // robots whose polish did not fit the fast kernel's buffer (> 2H stance leg-steps): every other
+  // CTA of this launch exits at once
+  mpc_solve_kernel<H, WARM, 12 * H, true><<<n, MPC_NL, KB::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, st,
+                                                                               resid, info, dbg, warm);
+  CK(cudaGetLastError());
+  if (!status) CK(cudaFreeAsync(st, stream));
+  return MPC_B200_OK;
+}
+
 template <int H>
 int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n,
            float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
            cudaStream_t stream) {
-  using K = KernelCfg<H>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    K::SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      K::SMEM_BYTES);
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
-  if (n <= 0) return MPC_B200_OK;
-  if (warm)
-    mpc_solve_kernel<H, true><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status,
-                                                                   resid, info, dbg, warm);
-  else
-    mpc_solve_kernel<H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, status,
-                                                                    resid, info, dbg, nullptr);
-  CK(cudaGetLastError());
-  return MPC_B200_OK;
+  if (warm) return launch_w<H, true>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, stream);
+  return launch_w<H, false>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, nullptr, stream);
 }
 
 int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int n,
@@ -366,8 +386,8 @@ int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int*
   if (regs_per_thread) {
     *regs_per_thread = -1;
     cudaFuncAttributes a;
-    cudaError_t e = horizon == 10 ? cudaFuncGetAttributes(&a, mpc_solve_kernel<10, false>)
-                                  : cudaFuncGetAttributes(&a, mpc_solve_kernel<16, false>);
+    cudaError_t e = horizon == 10 ? cudaFuncGetAttributes(&a, mpc_solve_kernel<10, false, 60, false>)
+                                  : cudaFuncGetAttributes(&a, mpc_solve_kernel<16, false, 96, false>);
     if (e == cudaSuccess) *regs_per_thread = a.numRegs;
     else cudaGetLastError();
   }

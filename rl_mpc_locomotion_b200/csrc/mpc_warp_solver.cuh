@@ -61,7 +61,7 @@ constexpr double kMinScale = 0.1;   // mpc_osqp.cc:56
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqFactor = 1e3, kRhoTol = 1e-4;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
 
-template <int H>
+template <int H, int PCAP_ = 6 * H>
 struct Dims {
   static constexpr int NL = MPC_NL;              // lanes (threads) cooperating on one robot
   static constexpr int NV = 12 * H;             // variables
@@ -70,7 +70,10 @@ struct Dims {
   static constexpr int NW = 6 * H;              // wrench-space dimension
   static constexpr int NWS = (NW + NL - 1) / NL;
   static constexpr int NVS = (NV + NL - 1) / NL;
-  static constexpr int NTRI = NW * (NW + 1) / 2;      // packed lower triangle (row i at i(i+1)/2; slot i of row i unused)
+  // polish capacity: free coordinates the on-chip polish can hold.  6H covers every contact table
+  // with <= 2H stance leg-steps (all of the reference's gaits); the overflow kernel uses 12H.
+  static constexpr int PCAP = PCAP_ < NW ? NW : PCAP_;
+  static constexpr int NTRI = PCAP * (PCAP + 1) / 2;  // packed lower triangle (row i at i(i+1)/2; slot i of row i unused)
   // shared-memory layout (doubles)
   static constexpr int OFF_WP = 0;                       // [NTRI] Hm -> L -> W = L^-1, row-packed
   static constexpr int OFF_SCR = OFF_WP + NTRI;          // scratch: vecA vecB vt vg vw Finv
@@ -80,17 +83,19 @@ struct Dims {
   static constexpr int OFF_VG = OFF_VT + NW;             // [NW]
   static constexpr int OFF_VW = OFF_VG + NW;             // [NW]
   static constexpr int OFF_FINV = OFF_VW + NW;           // [H][36]
-  static constexpr int SCR_SIZE = 2 * NV + 3 * NW + 36 * H;
-  static constexpr int OFF_DINV = OFF_SCR + SCR_SIZE;    // [NW] diag: H_ii -> 1/L_ii = W_ii
-  static constexpr int OFF_COL = OFF_DINV + NW;          // [2][NW] column staging (inversion, polish)
-  static constexpr int OFF_GAM = OFF_COL + 2 * NW;       // [H][H]
+  static constexpr int SCR_MIN = 2 * NV + 3 * NW + 36 * H;
+  static constexpr int SCR_POLISH = 12 * PCAP + PCAP / 2 + 8;   // Mf, A1f, kf of the polish
+  static constexpr int SCR_SIZE = SCR_MIN > SCR_POLISH ? SCR_MIN : ((SCR_POLISH + 1) & ~1);
+  static constexpr int OFF_DINV = OFF_SCR + SCR_SIZE;    // [PCAP] diag: H_ii -> 1/L_ii = W_ii
+  static constexpr int OFF_COL = OFF_DINV + PCAP;        // [2][PCAP] column staging (inversion, polish)
+  static constexpr int OFF_GAM = OFF_COL + 2 * PCAP;     // [H][H]
   static constexpr int OFF_NN = OFF_GAM + H * H;         // [H][H]
   static constexpr int OFF_WB = OFF_NN + H * H;          // [6][12] balanced wrench map
   static constexpr int OFF_Q1S = OFF_WB + 72;            // [6][6] Q1'
   static constexpr int OFF_Q2S = OFF_Q1S + 36;           // [6] diag of Q2' (+2 pad)
-  static constexpr int OFF_DSM = OFF_Q2S + 8;            // [NV] D (scaling) for broadcast reads
-  static constexpr int SMEM_DOUBLES = OFF_DSM + NV;
-  static_assert(12 * NW + NW / 2 + 8 <= SCR_SIZE, "polish scratch does not fit");
+  static constexpr int OFF_DSM = OFF_Q2S + 8;            // [max(NV, 2 PCAP)] D (scaling); polish vectors
+  static constexpr int SMEM_DOUBLES = OFF_DSM + (NV > 2 * PCAP ? NV : 2 * PCAP);
+  static_assert(SCR_POLISH <= SCR_SIZE, "polish scratch does not fit");
   static_assert(NLS * 21 <= NTRI && 288 + 72 <= NTRI, "staging does not fit in the triangle buffer");
 };
 
@@ -175,13 +180,13 @@ MPC_LANEFN void inv6spd(const double* a, double* out) {
 // OFF_GAM/OFF_NN must have been filled by fill_tables<H>() before the first call.
 // Outputs: grf0[12] (negated horizon-0 forces), grf_full[12H] or null, status, info or null.
 // ---------------------------------------------------------------------------------------
-template <int H>
+template <int H, int PCAP_ = 6 * H>
 MPC_FN void fill_tables(double* sm, double dt
 #if defined(__CUDACC__) && !defined(MPC_EMULATE)
                         , const int lane
 #endif
 ) {
-  using D = Dims<H>;
+  using D = Dims<H, PCAP_>;
   LANES_BEGIN
   for (int e = lane; e < H * H; e += NL) {
     const int i = e / H, j = e % H;
@@ -196,7 +201,7 @@ MPC_FN void fill_tables(double* sm, double dt
   WSYNC();
 }
 
-template <int H, bool WARM = false>
+template <int H, bool WARM = false, int PCAP_ = 6 * H>
 MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& prm, double* sm,
                         float* grf0, float* grf_full, int32_t* status_out, float* resid_out,
                         double* info_out, double* dbg_out, double* warm
@@ -204,16 +209,25 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
                         , const int lane
 #endif
 ) {
-  using D = Dims<H>;
+  using D = Dims<H, PCAP_>;
+  constexpr int PCAP = D::PCAP;
   // `warm` (MPC_WARM_STRIDE(H) doubles in global memory, or null): OSQP's persistent workspace
   // state between consecutive solves of the same robot (settings.warm_start, mpc_osqp.cc:708,
-  // :760-778): [0] valid flag, [1] rho, then x[12h], z[20h], y[20h] (scaled iterates, left as
-  // they are when the data is re-scaled, exactly as osqp_update_P_A does) and the previous
-  // UNSCALED q[12h] (osqp_update_P_A re-runs scale_data before osqp_update_lin_cost installs the
-  // new q, so the cost normalisation c sees the OLD q).
+  // :760-778): [0] flag (0 = none yet, 1 / 2 = which q slot holds the previous problem's q),
+  // [1] rho, then x[12h], z[20h], y[20h] (scaled iterates, left as they are when the data is
+  // re-scaled, exactly as osqp_update_P_A does) and two slots of UNSCALED q[12h]: osqp_update_P_A
+  // re-runs scale_data before osqp_update_lin_cost installs the new q, so the cost normalisation
+  // c sees the OLD q.  The new q goes to the other slot and the flag flips only when the solve
+  // completes, so a robot handed to the overflow kernel is re-solved from the same state.
   // WARM is a compile-time switch so that the cold-start kernel carries none of this code.
   bool warm_valid = false;
-  if constexpr (WARM) warm_valid = warm != nullptr && warm[0] != 0.0;
+  int q_prev_off = 0, q_new_off = 0;
+  if constexpr (WARM) {
+    warm_valid = warm != nullptr && warm[0] != 0.0;
+    const bool prev_in_b = warm != nullptr && warm[0] == 2.0;
+    q_prev_off = 2 + 52 * H + (prev_in_b ? 12 * H : 0);
+    q_new_off = 2 + 52 * H + (prev_in_b ? 0 : (warm_valid ? 12 * H : 0));
+  }
   constexpr int NS = D::NSLOT, NW = D::NW, NV = D::NV;
   double* const Wp = sm + D::OFF_WP;
   double* const vecA = sm + D::OFF_VECA;
@@ -453,8 +467,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       if constexpr (WARM) {
         if (warm && _(valid)[s]) {
           // the workspace keeps the UNSCALED q; scale_data below must see the OLD one (if any)
-          if (warm_valid) _(qb)[s][a] = warm[2 + 52 * H + 3 * j + a];
-          warm[2 + 52 * H + 3 * j + a] = qn;
+          if (warm_valid) _(qb)[s][a] = warm[q_prev_off + 3 * j + a];
+          warm[q_new_off + 3 * j + a] = qn;
         }
       }
       _(Dv)[s][a] = 1.0;
@@ -690,7 +704,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   // L is staged in colb (double buffered) because its owners overwrite it with W.
   auto invert_lower = [&](int n) {
     for (int j = n - 2; j >= 0; --j) {
-      double* const buf = colb + (j & 1) * NW;
+      double* const buf = colb + (j & 1) * PCAP;
       LANES_BEGIN
       for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) buf[i] = Wp[tri(i) + j];
       LANES_END
@@ -993,7 +1007,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           // osqp_update_lin_cost: q = c * (D .* q_new)   (osqp.c:752-782)
-          _(qb)[s][a] = (_(Dv)[s][a] * warm[2 + 52 * H + 3 * j + a]) * cscale;
+          _(qb)[s][a] = (_(Dv)[s][a] * warm[q_new_off + 3 * j + a]) * cscale;
           _(xv)[s][a] = warm[2 + 3 * j + a];
         }
 #pragma unroll
@@ -1274,11 +1288,11 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WEXSCAN_I(off, cnt);
     nfree_total = WSUM_I(cnt);
-    if (nfree_total <= NW) {
+    if (nfree_total <= PCAP) {
       const int nf = nfree_total;
       double* const Mf = sm + D::OFF_SCR;            // [nf][6]  m_f = U nu_f
-      double* const A1f = Mf + 6 * NW;               // [nf][6]  Q1' m_f
-      int* const kf = reinterpret_cast<int*>(A1f + 6 * NW);  // [nf] step index
+      double* const A1f = Mf + 6 * PCAP;             // [nf][6]  Q1' m_f
+      int* const kf = reinterpret_cast<int*>(A1f + 6 * PCAP);  // [nf] step index
       // gP = Pbar p + qbar  (needs apply_P before the scratch is overwritten)
       LANES_BEGIN
 #pragma unroll
@@ -1385,11 +1399,11 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       cholesky(nf);
       // polish vectors: Dsm is free here (D is also held in registers), colb holds xi_0
       double* const pv = Dsm;        // [nf] right-hand side / solution of the triangular solves
-      double* const pxi = Dsm + NW;  // [nf] current xi
+      double* const pxi = Dsm + PCAP;  // [nf] current xi
       double* const pxi0 = colb;     // [nf] first regularised solve (colb is free again after invert_lower)
       invert_lower(nf);             // W = L^-1: every solve below is two barrier-light mat-vecs
       auto tri_solve = [&]() {      // pv <- W^T (W pv) = (L L^T)^-1 pv
-        double* const ty = colb + NW;
+        double* const ty = colb + PCAP;
         LANES_BEGIN
         for (int i = lane; i < nf; i += NL) {
           const double* rowi = Wp + tri(i);
@@ -1565,7 +1579,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         polish_status = -1;
       }
     } else {
-      polish_status = -1;  // free set larger than the on-chip buffer (never for reference gaits)
+      polish_status = -1;  // free set larger than this instantiation's polish capacity
+      status = MPC_STATUS_POLISH_OVERFLOW;   // the overflow kernel (PCAP = 12H) re-solves this robot
     }
   }
 
@@ -1584,7 +1599,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
     }
   }
-  if constexpr (WARM) if (warm) {   // leave the workspace state for the next solve (scaled iterates, rho)
+  if constexpr (WARM) if (warm && status != MPC_STATUS_POLISH_OVERFLOW) {   // workspace state for the next solve
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s]) {
@@ -1598,7 +1613,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         }
       }
     if (lane == 0) {
-      warm[0] = 1.0;
+      warm[0] = (q_new_off == 2 + 52 * H) ? 1.0 : 2.0;   // the slot just written becomes "previous"
       warm[1] = rho;
     }
   }

@@ -47,7 +47,7 @@ class BatchedLocomotion:
         # OSQP workspace state per robot: the reference's OSQP branch keeps one workspace per
         # ConvexMpc object and warm-starts every tick (mpc_osqp.cc:757-778); off by default
         # (cold start = the golden-vector semantics)
-        self.warm = torch.zeros((self.n, 2 + 64 * horizon), dtype=torch.float64, device=dev) if warm_start else None
+        self.warm = torch.zeros((self.n, 2 + 76 * horizon), dtype=torch.float64, device=dev) if warm_start else None
 
     @property
     def unsafe(self) -> torch.Tensor:

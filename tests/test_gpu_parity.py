@@ -134,3 +134,20 @@ def test_warm_start_sequence_on_device(oracle_mod):
         torch.cuda.synchronize()
         assert int(out["info"][0, 0]) == o.last_iters and int(out["status"][0]) == st
         assert np.abs(out["grf_full"][0].cpu().numpy() - f).max() < TOL_N
+
+
+@pytest.mark.parametrize("horizon", [10, 16])
+def test_standing_contact_table_uses_overflow_kernel(oracle_mod, horizon):
+    """All 4h leg-steps in stance: up to 12h free polish coordinates, beyond the fast kernel's
+    buffer -> MPC_STATUS_POLISH_OVERFLOW internally, re-solved by the PCAP = 12h instantiation in
+    the same call.  The caller must only ever see OSQP's status and the reference's forces."""
+    from rl_mpc_locomotion_b200 import synth
+    from rl_mpc_locomotion_b200.records import REC_CONTACT
+    rec, rt, params, _ = synth.make_batch(48, horizon, seed=9)
+    rec = rec.copy()
+    rec[:, REC_CONTACT:REC_CONTACT + 4 * horizon] = 1.0
+    out = _gpu_solve(rec, rt, params, horizon)
+    f0, ff, st = oracle_mod.solve_records(rec, horizon, params, rt, mode=oracle_mod.COLD, full=True)
+    assert (out["status"] == st).all() and (out["status"] == 1).all()
+    assert np.abs(out["grf_full"] - ff).max() < TOL_N
+    assert out["info"][:, 7].max() > 6 * horizon      # the overflow path was really exercised

@@ -82,7 +82,7 @@ def test_device_estimator_reproduces_float16_outputs_bit_for_bit():
 def test_tick_replay_with_warm_started_osqp_workspace():
     """The reference's OSQP branch keeps ONE workspace per robot and warm-starts every MPC tick
     (mpc_osqp.cc:757-778); fixture recorded with the oracle module in WARM mode."""
-    warm = np.zeros((1, 2 + 64 * 10))
+    warm = np.zeros((1, 2 + 76 * 10))
     w = replay("aliengo_trot_warm", _emu_tick, device_estimator=True, warm=warm)
     print(w)
     assert w["rec"] < 5e-6 and w["fff"] < 5e-3 and w["tau"] < 2e-3

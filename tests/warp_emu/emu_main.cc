@@ -15,17 +15,27 @@ template <int H>
 static void run(const float* rec, int n, const float* rp, const int* rt, const mpc::SolveParams& prm,
                 float* grf0, float* grf_full, int32_t* status, double* info, double* dbg, double* warm) {
   using D = mpc::Dims<H>;
-  std::vector<double> sm(D::SMEM_DOUBLES, 0.0);
+  using DB = mpc::Dims<H, 12 * H>;
+  std::vector<double> sm(D::SMEM_DOUBLES, 0.0), smb(DB::SMEM_DOUBLES, 0.0);
   mpc::fill_tables<H>(sm.data(), prm.dt);
+  mpc::fill_tables<H, 12 * H>(smb.data(), prm.dt);
   const int stride = MPC_REC_STRIDE(H);
   const int dbg_stride = D::NV + D::NV * D::NV + D::NV + 20 * H + 1;
   for (int r = 0; r < n; ++r) {
     const float* rpr = rp + (size_t)(rt ? rt[r] : 0) * MPC_ROBOT_PARAMS_STRIDE;
+    int32_t st = 0;
     mpc::solve_robot<H, true>(rec + (size_t)r * stride, rpr, prm, sm.data(), grf0 + (size_t)r * 12,
-                        grf_full ? grf_full + (size_t)r * 12 * H : nullptr, status ? status + r : nullptr,
+                        grf_full ? grf_full + (size_t)r * 12 * H : nullptr, &st,
                         nullptr, info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr,
                         dbg ? dbg + (size_t)r * dbg_stride : nullptr,
                         warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+    if (st == MPC_STATUS_POLISH_OVERFLOW)   // the overflow kernel's job on the device
+      mpc::solve_robot<H, true, 12 * H>(rec + (size_t)r * stride, rpr, prm, smb.data(), grf0 + (size_t)r * 12,
+                          grf_full ? grf_full + (size_t)r * 12 * H : nullptr, &st,
+                          nullptr, info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr,
+                          dbg ? dbg + (size_t)r * dbg_stride : nullptr,
+                          warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+    if (status) status[r] = st;
   }
 }
 
