@@ -65,7 +65,8 @@ extern "C" {
 /* per-robot status written by the kernel (int32) */
 #define MPC_STATUS_SOLVED          1   /* mirrors OSQP_SOLVED (constants.h)   */
 #define MPC_STATUS_MAX_ITER       -2   /* mirrors OSQP_MAX_ITER_REACHED       */
-#define MPC_STATUS_NON_FINITE     -7   /* NaN/Inf met -> forces zeroed        */
+#define MPC_STATUS_NON_FINITE     -7   /* residuals diverged / NaN (mirrors OSQP_NON_CVX): forces zeroed,
+                                          warm state untouched; the reference returns an empty vector   */
 #define MPC_STATUS_POLISH_OVERFLOW -90 /* internal: more free coordinates than the fast kernel's polish
                                           buffer (> 2h stance leg-steps); re-solved by the overflow kernel
                                           inside the same mpc_b200_solve_batch call, never returned    */

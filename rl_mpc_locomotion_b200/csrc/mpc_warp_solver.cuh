@@ -1134,6 +1134,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     pri_res = nr_[0];
     dua_res = cinv * nr_[1];
+    if (!(pri_res <= 1e30) || !(dua_res <= 1e30)) {   // diverged / NaN: OSQP_NON_CVX (auxil.c:697-704)
+      status = MPC_STATUS_NON_FINITE;
+      break;
+    }
     if (prm.fixed_iters <= 0) {
       const double eps_prim = prm.eps_abs + prm.eps_rel * fmax(nr_[2], nr_[3]);
       const double eps_dual = prm.eps_abs + prm.eps_rel * cinv * fmax(fmax(nr_[4], nr_[5]), nr_[6]);
@@ -1585,6 +1589,21 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   }
 
   // ------------------------------------------------------------------ S6: output
+  // NaN / Inf inputs slip through OSQP's inf-norms (comparisons with NaN are false) and would
+  // come back as NaN forces; report them instead
+  LANES_BEGIN
+  double bad = 0.0;
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    if (_(valid)[s])
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double v = _(Dv)[s][a] * _(xv)[s][a];
+        if (!(fabs(v) <= 1e30)) bad = 1.0;
+      }
+  _(red) = bad;
+  LANES_END
+  if (WMAX(red) != 0.0) status = MPC_STATUS_NON_FINITE;
   // unscale (scaling.c:183-199) and negate (mpc_osqp.cc:789-790)
   LANES_BEGIN
 #pragma unroll
@@ -1593,13 +1612,14 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       const int j = lane + NL * s;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const float f = (float)(-_(Dv)[s][a] * _(xv)[s][a]);
+        // no solution (OSQP_NON_CVX): the reference returns an empty vector; we return zeros
+        const float f = status == MPC_STATUS_NON_FINITE ? 0.0f : (float)(-_(Dv)[s][a] * _(xv)[s][a]);
         if (j < 4) grf0[3 * j + a] = f;
         if (grf_full) grf_full[3 * j + a] = f;
       }
     }
   }
-  if constexpr (WARM) if (warm && status != MPC_STATUS_POLISH_OVERFLOW) {   // workspace state for the next solve
+  if constexpr (WARM) if (warm && status != MPC_STATUS_POLISH_OVERFLOW && status != MPC_STATUS_NON_FINITE) {
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (_(valid)[s]) {

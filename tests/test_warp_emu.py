@@ -117,3 +117,13 @@ def test_contact_tables_outside_the_reference_gaits(oracle_mod, name, table):
     f0, ff, st = oracle_mod.solve_records(rec, 10, params, rt, mode=oracle_mod.COLD, full=True)
     assert np.array_equal(out["status"], st)
     assert np.abs(out["grf_full"] - ff).max() < 1e-3
+
+
+def test_non_finite_input_is_reported_not_propagated():
+    rec, rt, params, _ = synth.make_batch(3, 10, seed=2)
+    rec = rec.copy()
+    rec[1, 16] = np.nan                      # com_velocity[0] of robot 1
+    out = emu.solve(rec, 10, params, rt)
+    assert out["status"][0] == 1 and out["status"][2] == 1
+    assert out["status"][1] == -7 and np.all(out["grf_full"][1] == 0)
+    assert np.isfinite(out["grf_full"]).all()
