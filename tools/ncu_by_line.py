@@ -11,7 +11,7 @@ tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 txt = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(txt) if l.startswith(".text.") and f"mpc_solve_kernelILi{H}ELb0" in l][0]
+start = [i for i, l in enumerate(txt) if l.startswith(".text.") and f"mpc_solve_kernelILi{H}ELb0ELi{6*int(H)}ELb0" in l][0]
 cur, seq = None, []
 for l in txt[start + 1:]:
     if (l.startswith("//---------------------") or l.startswith("\t.section")) and seq:
