@@ -265,7 +265,9 @@ def main():
     line = {"metric": "QP solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "solved_fraction": n_solved / n_per_gpu, "gpu_launches": args.steps, "clocks": clocks,
+            "solved_fraction": n_solved / n_per_gpu,
+            # per step: the solve kernel + the (10 us, all CTAs exit) polish-overflow instantiation
+            "gpu_launches": 2 * args.steps, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "mpc_b200_solve_batch_host (C-ABI, pinned host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
