@@ -236,6 +236,26 @@ def main():
                  "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3), "unit": "solves/s",
                  "note": "fixed 50 ADMM iterations, no termination test / polish (side measurement, rank 0)"}
 
+    # ---- side measurement: the headline solve again, launched longest-first using the iteration
+    # counts of a previous solve of the same robots (the d_order scheduling hint; identical results).
+    lpt = None
+    if args.mode == "osqp":
+        from rl_mpc_locomotion_b200.batched import lpt_order
+        order = lpt_order(mpc.solve(d_rec, d_rt, info=True)["info"])
+        for _ in range(3):
+            mpc.solve(d_rec, d_rt, out=d_out, order=order)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(5):
+            mpc.solve(d_rec, d_rt, out=d_out, order=order)
+        f1.record()
+        torch.cuda.synchronize()
+        lpt = {"ms_per_step": f0.elapsed_time(f1) / 5, "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3),
+               "unit": "solves/s",
+               "note": "same OSQP-faithful solve, CTAs launched in descending order of the previous solve's "
+                       "iteration counts (perfect prediction here because the batch repeats; side measurement, rank 0)"}
+
     # ---- e2e: C-ABI host entry point, pinned host buffers, copies inside the timed region
     from rl_mpc_locomotion_b200.batched import solve_host_pinned
     e2e_steps = max(3, min(args.steps, 10))
@@ -280,6 +300,8 @@ def main():
                                  "instruction issue/latency and shared-memory bandwidth (DESIGN.md §7)"}}
     if fixed is not None:
         line["fixed_iteration_mode"] = fixed
+    if lpt is not None:
+        line["longest_first_launch_order"] = lpt
     if not args.no_cpu_baseline:
         v, wall, sample = cpu_reference_rate(rec, rt, params, h, cores)
         line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",

@@ -131,6 +131,11 @@ int  mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta,
  *                  workspace state (settings.warm_start = true, mpc_osqp.cc:708, :760-778).
  *                  Rows with flag 0 start cold (= osqp_setup on the first call); every solve
  *                  leaves its iterates / rho / q for the next one.  NULL = cold start always.
+ *   d_order        [n_robots] int32 device or NULL: launch order (CTA b solves robot d_order[b]).
+ *                  Purely a scheduling hint - results are identical: OSQP's iteration count varies
+ *                  50..350 per robot and the launch ends with its slowest robot, so a control loop
+ *                  can pass last tick's robots sorted by descending iteration count
+ *                  (longest-processing-time-first) to shorten the tail.  NULL = index order.
  *   stream         cudaStream_t as void* (NULL = legacy default stream)
  * Asynchronous w.r.t. the host.
  */
@@ -145,6 +150,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings,
                          float* d_resid,
                          double* d_info,
                          double* d_warm,
+                         const int32_t* d_order,
                          void* stream);
 
 /*

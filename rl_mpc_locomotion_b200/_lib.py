@@ -59,7 +59,7 @@ def lib():
         L.mpc_b200_device_count.restype = C.c_int
         L.mpc_b200_kernel_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.mpc_b200_kernel_info.restype = C.c_int
-        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_solve_batch.restype = C.c_int
         L.mpc_b200_solve_batch_host.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp]
         L.mpc_b200_solve_batch_host.restype = C.c_int

@@ -44,7 +44,7 @@ class BatchedConvexMpc:
 
     def solve(self, records: torch.Tensor, robot_type: torch.Tensor | None = None, *, full: bool = False,
               status: bool = True, info: bool = False, out: torch.Tensor | None = None,
-              warm: torch.Tensor | None = None) -> dict:
+              warm: torch.Tensor | None = None, order: torch.Tensor | None = None) -> dict:
         """``records`` [N, stride] float32 CUDA tensor -> dict(grf0[N,12], grf_full?, status?, resid, info?).
 
         ``grf0`` is the negated horizon-0 QP solution, i.e. exactly ``result[0:12]`` of the
@@ -67,11 +67,13 @@ class BatchedConvexMpc:
         if warm is not None:
             assert warm.is_cuda and warm.dtype == torch.float64 and warm.is_contiguous()
             assert tuple(warm.shape) == (n, 2 + 76 * self.horizon), warm.shape
+        if order is not None:   # scheduling hint (longest-first), see lpt_order()
+            assert order.is_cuda and order.dtype == torch.int32 and order.shape == (n,) and order.is_contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = _lib.lib().mpc_b200_solve_batch(C.byref(self.settings), ptr(records), ptr(self.robot_params),
                                                  ptr(robot_type), n, ptr(grf0), ptr(gfull), ptr(st),
-                                                 ptr(resid), ptr(inf), ptr(warm), C.c_void_p(stream))
+                                                 ptr(resid), ptr(inf), ptr(warm), ptr(order), C.c_void_p(stream))
         _lib.check(rc, "mpc_b200_solve_batch")
         if full:
             res["grf_full"] = gfull
@@ -80,6 +82,14 @@ class BatchedConvexMpc:
         if info:
             res["info"] = inf
         return res
+
+
+def lpt_order(info: torch.Tensor) -> torch.Tensor:
+    """Launch order for the NEXT solve of the same robots from THIS solve's ``info``: robots sorted
+    by descending OSQP iteration count (longest-processing-time-first).  Consecutive control ticks
+    of a robot need similar iteration counts, so this shortens the tail of the launch; results are
+    unaffected."""
+    return torch.argsort(info[:, 0], descending=True, stable=True).to(torch.int32)
 
 
 def solve_host(records: np.ndarray, horizon: int = 10, robot_params=None, robot_type=None, full=False,

@@ -88,7 +88,7 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                  const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
                  int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
                  int32_t* __restrict__ status, float* __restrict__ resid, double* __restrict__ info,
-                 double* __restrict__ dbg, double* __restrict__ warm) {
+                 double* __restrict__ dbg, double* __restrict__ warm, const int32_t* __restrict__ order) {
   using K = KernelCfg<H, PCAP>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -96,8 +96,8 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
   float* rp_s = reinterpret_cast<float*>(smem_raw + K::OFF_RP);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);
   const int lane = threadIdx.x;
-  const int robot = blockIdx.x;
-  if (robot >= n_robots) return;
+  if ((int)blockIdx.x >= n_robots) return;
+  const int robot = order ? order[blockIdx.x] : (int)blockIdx.x;   // scheduling hint only
   if constexpr (ONLY_OVERFLOW) {
     if (status[robot] != MPC_STATUS_POLISH_OVERFLOW) return;   // uniform per CTA
   }
@@ -274,7 +274,7 @@ int check_settings(const MpcB200Settings* s) {
 template <int H, bool WARM>
 int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n, float* grf0,
              float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
-             cudaStream_t stream) {
+             const int32_t* order, cudaStream_t stream) {
   using K = KernelCfg<H>;
   using KB = KernelCfg<H, 12 * H>;
   static std::once_flag once;
@@ -292,12 +292,12 @@ int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, con
   int32_t* st = status;
   if (!st) CK(cudaMallocAsync((void**)&st, (size_t)n * sizeof(int32_t), stream));
   mpc_solve_kernel<H, WARM, 6 * H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, st,
-                                                                               resid, info, dbg, warm);
+                                                                               resid, info, dbg, warm, order);
   CK(cudaGetLastError());
   // robots whose polish did not fit the fast kernel's buffer (> 2H stance leg-steps): every other
   // CTA of this launch exits at once
   mpc_solve_kernel<H, WARM, 12 * H, true><<<n, MPC_NL, KB::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, st,
-                                                                               resid, info, dbg, warm);
+                                                                               resid, info, dbg, warm, order);
   CK(cudaGetLastError());
   if (!status) CK(cudaFreeAsync(st, stream));
   return MPC_B200_OK;
@@ -306,18 +306,19 @@ int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, con
 template <int H>
 int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n,
            float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
-           cudaStream_t stream) {
-  if (warm) return launch_w<H, true>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, stream);
-  return launch_w<H, false>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, nullptr, stream);
+           const int32_t* order, cudaStream_t stream) {
+  if (warm)
+    return launch_w<H, true>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
+  return launch_w<H, false>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, nullptr, order, stream);
 }
 
 int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int n,
              float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
-             cudaStream_t stream) {
+             const int32_t* order, cudaStream_t stream) {
   const mpc::SolveParams prm = to_params(*s);
   if (s->horizon == 10)
-    return launch<10>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, stream);
-  return launch<16>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, stream);
+    return launch<10>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
+  return launch<16>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
 }
 
 // grow-only device scratch for the host-pointer convenience entry points
@@ -397,7 +398,7 @@ int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int*
 int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records,
                          const float* d_robot_params, const int32_t* d_robot_type, int n_robots,
                          float* d_grf0, float* d_grf_full, int32_t* d_status, float* d_resid,
-                         double* d_info, double* d_warm, void* stream) {
+                         double* d_info, double* d_warm, const int32_t* d_order, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
   if (n_robots < 0 || (n_robots > 0 && (!d_records || !d_robot_params || !d_grf0))) {
@@ -410,7 +411,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records
   }
   if (n_robots == 0) return MPC_B200_OK;
   return dispatch(settings, d_records, d_robot_params, d_robot_type, n_robots, d_grf0, d_grf_full, d_status,
-                  d_resid, d_info, nullptr, d_warm, (cudaStream_t)stream);
+                  d_resid, d_info, nullptr, d_warm, d_order, (cudaStream_t)stream);
 }
 
 int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_records,
@@ -453,7 +454,8 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_re
                      cudaMemcpyHostToDevice, st));
   if (h_robot_type) CK(cudaMemcpyAsync(d_rt, h_robot_type, (size_t)n_robots * 4, cudaMemcpyHostToDevice, st));
   rc = dispatch(settings, d_rec, d_rp, h_robot_type ? d_rt : nullptr, n_robots, d_g0,
-                h_grf_full ? d_gf : nullptr, h_status ? d_st : nullptr, nullptr, nullptr, nullptr, nullptr, st);
+                h_grf_full ? d_gf : nullptr, h_status ? d_st : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_grf0, d_g0, (size_t)n_robots * 12 * 4, cudaMemcpyDeviceToHost, st));
   if (h_grf_full) CK(cudaMemcpyAsync(h_grf_full, d_gf, (size_t)n_robots * 12 * h * 4, cudaMemcpyDeviceToHost, st));
@@ -520,7 +522,8 @@ int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_reco
   CK(cudaMalloc(&d_dbg, ndbg * 8));
   CK(cudaMemcpy(d_rec, h_record, MPC_REC_STRIDE(h) * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_rp, h_robot_params, MPC_ROBOT_PARAMS_STRIDE * 4, cudaMemcpyHostToDevice));
-  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr, nullptr);
+  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr, nullptr,
+                nullptr);
   if (rc == MPC_B200_OK) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = cuda_fail(e, "debug kernel");

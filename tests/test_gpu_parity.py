@@ -151,3 +151,18 @@ def test_standing_contact_table_uses_overflow_kernel(oracle_mod, horizon):
     assert (out["status"] == st).all() and (out["status"] == 1).all()
     assert np.abs(out["grf_full"] - ff).max() < TOL_N
     assert out["info"][:, 7].max() > 6 * horizon      # the overflow path was really exercised
+
+
+def test_launch_order_hint_does_not_change_results():
+    import torch
+    from rl_mpc_locomotion_b200 import synth
+    from rl_mpc_locomotion_b200.batched import BatchedConvexMpc, lpt_order
+    rec, rt, params, _ = synth.make_batch(300, 10, seed=4)
+    mpc = BatchedConvexMpc(10, device="cuda:0", robot_params=params)
+    d_rec, d_rt = torch.from_numpy(rec).cuda(), torch.from_numpy(rt).cuda()
+    a = mpc.solve(d_rec, d_rt, full=True, info=True)
+    order = lpt_order(a["info"])
+    assert sorted(order.cpu().tolist()) == list(range(300))
+    b = mpc.solve(d_rec, d_rt, full=True, info=True, order=order)
+    torch.cuda.synchronize()
+    assert torch.equal(a["grf_full"], b["grf_full"]) and torch.equal(a["status"], b["status"])

@@ -77,7 +77,7 @@ def test_no_cpu_fallback():
         solve_host(rec, 10, robot_params=params, robot_type=rt)
     with pytest.raises(_lib.MpcB200Error):
         _lib.check(_lib.lib().mpc_b200_solve_batch(C.byref(_lib.default_settings(horizon=12)), None, None, None,
-                                                   0, None, None, None, None, None, None, None), "bad horizon")
+                                                   0, None, None, None, None, None, None, None, None), "bad horizon")
 
 
 def test_product_does_not_import_oracle():
