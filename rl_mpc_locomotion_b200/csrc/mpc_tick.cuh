@@ -29,11 +29,6 @@
 
 #if defined(__CUDACC__) && !defined(MPC_EMULATE)
 #include <cuda_fp16.h>
-#define MPC_LANE_ARG , const int lane
-#define MPC_LANE_PASS , lane
-#else
-#define MPC_LANE_ARG
-#define MPC_LANE_PASS
 #endif
 
 namespace mpc {

@@ -175,6 +175,158 @@ MPC_LANEFN void inv6spd(const double* a, double* out) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Dense factorisation kernels of the wrench-space / polish systems (shared memory only).
+// ---------------------------------------------------------------------------------------
+constexpr int kFactorBlock = 6;
+#if defined(__CUDACC__) && !defined(MPC_EMULATE)
+#define MPC_RSQRT(x) rsqrt(x)
+#else
+#define MPC_RSQRT(x) (1.0 / std::sqrt(x))
+#endif
+
+  // Blocked dense Cholesky (left-looking by block columns of width CB) of the leading n x n block,
+  // n a multiple of CB, held as: strictly-lower triangle in Wp (row-packed), diagonal in colb[0..n).
+  // On exit Wp holds L (strictly lower), dinv[i] = 1/L_ii.  Row i is owned by lane i % NL.
+  // Per block column: (1) every row at or below the block subtracts the contribution of the
+  // finished columns from its CB entries - CB independent dot products that share the load of the
+  // row's own element; the rows of the diagonal block park theirs in `stage`; (2) every lane
+  // factorises the CB x CB diagonal block redundantly in registers (same latency as one lane doing
+  // it, no third barrier) while forward-substituting its own row.  Two barriers per block column.
+template <int PCAP>
+MPC_NOINLINE_FN void cholesky_blocked(double* Wp, double* colb, double* dinv, int n MPC_LANE_ARG) {
+  constexpr int NL = MPC_NL, CB = kFactorBlock;
+  {
+    double* const hdiag = colb;
+    double* const stage = colb + PCAP;  // [CB(CB+1)/2] updated diagonal block, row-packed with diagonal
+    for (int J = 0; J < n; J += CB) {
+      const double* const pj = Wp + tri(J);  // row J+c starts at pj + c*J + c(c+1)/2
+      LANES_BEGIN
+      for (int i = lane; i < n; i += NL) {
+        if (i < J) continue;
+        double* const rowi = Wp + tri(i);
+        const int r = i - J;  // < CB: a row of the diagonal block
+        double acc[CB];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) acc[c] = (c < r) ? rowi[J + c] : (c == r ? hdiag[i] : 0.0);
+#pragma unroll 2
+        for (int k = 0; k < J; ++k) {
+          const double li = rowi[k];
+#pragma unroll
+          for (int c = 0; c < CB; ++c) acc[c] -= li * pj[c * J + (c * (c + 1)) / 2 + k];
+        }
+        if (r < CB) {
+#pragma unroll
+          for (int c = 0; c < CB; ++c)
+            if (c <= r) stage[tri(r) + c] = acc[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < CB; ++c) rowi[J + c] = acc[c];
+        }
+      }
+      LANES_END
+      WSYNC();
+      LANES_BEGIN
+      for (int i = lane; i < n; i += NL) {
+        if (i < J) continue;
+        double* const rowi = Wp + tri(i);
+        const int r = i - J;
+        double S[CB * (CB + 1) / 2], x[CB];
+#pragma unroll
+        for (int e = 0; e < CB * (CB + 1) / 2; ++e) S[e] = stage[e];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) x[c] = (r >= CB) ? rowi[J + c] : (c <= r ? stage[tri(r) + c] : 0.0);
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {  // right-looking on the register copy; x rides along
+          const double inv = MPC_RSQRT(S[tri(c) + c]);
+          if (c == r) dinv[i] = inv;
+          x[c] *= inv;
+#pragma unroll
+          for (int r1 = c + 1; r1 < CB; ++r1) {
+            S[tri(r1) + c] *= inv;
+            x[r1] -= x[c] * S[tri(r1) + c];
+          }
+#pragma unroll
+          for (int r1 = c + 1; r1 < CB; ++r1)
+#pragma unroll
+            for (int r2 = c + 1; r2 <= r1; ++r2) S[tri(r1) + r2] -= S[tri(r1) + c] * S[tri(r2) + c];
+        }
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+          if (J + c < i) rowi[J + c] = x[c];
+      }
+      LANES_END
+      WSYNC();
+    }
+  }
+}
+
+  // in-place inverse of the lower factor: W = L^-1 (strictly-lower part in Wp, W_ii = dinv[i]), by
+  // block columns J = n-CB .. 0:  W_IJ = -(sum_{K>J} W_IK L_KJ) L_JJ^-1.  A row accumulates its CB
+  // sums (independent chains), back-substitutes through L_JJ and holds the result in registers
+  // across the single barrier of the step (every other row's L_KJ must have been read before its
+  // owner overwrites it); the next step reads only columns left of J, so no second barrier.
+template <int PCAP>
+MPC_NOINLINE_FN void invert_lower_blocked(double* Wp, const double* dinv, int n MPC_LANE_ARG) {
+  constexpr int NL = MPC_NL, CB = kFactorBlock;
+  constexpr int NRS = (PCAP + NL - 1) / NL;  // rows of the dense factor per lane
+  {
+    PER_LANE_ARR(double, Tw, [NRS][CB]);
+    for (int J = n - CB; J >= 0; J -= CB) {
+      const double* const pj = Wp + tri(J) + J;  // L_JJ[c2][c] = pj[c2*J + c2(c2+1)/2 + c]
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NRS; ++s) {
+        const int i = lane + NL * s;
+        if (i >= J && i < n) {
+          const double* const rowi = Wp + tri(i);
+          const int r = i - J;
+          double S[CB];
+          if (r < CB) {  // a row of L_JJ^-1 itself: e_r L_JJ^-1
+#pragma unroll
+            for (int c = 0; c < CB; ++c) S[c] = (c == r) ? -1.0 : 0.0;
+          } else {
+            const double di = dinv[i];
+#pragma unroll
+            for (int c = 0; c < CB; ++c) S[c] = di * rowi[J + c];
+            const double* p = Wp + tri(J + CB) + J;  // &L[k][J]
+#pragma unroll 2
+            for (int k = J + CB; k < i; ++k) {
+              const double w = rowi[k];
+#pragma unroll
+              for (int c = 0; c < CB; ++c) S[c] += w * p[c];
+              p += k + 1;
+            }
+          }
+#pragma unroll
+          for (int c = CB - 1; c >= 0; --c) {  // T L_JJ = -S
+            double t = -S[c];
+#pragma unroll
+            for (int c2 = c + 1; c2 < CB; ++c2) t -= _(Tw)[s][c2] * pj[c2 * J + (c2 * (c2 + 1)) / 2 + c];
+            _(Tw)[s][c] = t * dinv[J + c];
+          }
+        }
+      }
+      LANES_END
+      WSYNC();
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NRS; ++s) {
+        const int i = lane + NL * s;
+        if (i >= J && i < n) {
+          double* const rowi = Wp + tri(i);
+#pragma unroll
+          for (int c = 0; c < CB; ++c)
+            if (J + c < i) rowi[J + c] = _(Tw)[s][c];
+        }
+      }
+      LANES_END
+    }
+    WSYNC();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
 // The solver.  `rec` = problem record (float, MPC_REC_* layout), `rp` = robot constant row.
 // `sm` = this warp's shared-memory block (Dims<H>::SMEM_DOUBLES doubles); Gamma/N tables at
 // OFF_GAM/OFF_NN must have been filled by fill_tables<H>() before the first call.
@@ -523,7 +675,9 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_BEGIN
     for (int v = lane; v < NV; v += NL) {
       const int k2 = v / 12, b = v % 12;
+#pragma unroll 1
       for (int k = 0; k < H; ++k)
+#pragma unroll 1
         for (int a = 0; a < 12; ++a) {
           double p = 2.0 * (gam[k * H + k2] * G1[a * 12 + b] + nnm[k * H + k2] * G2[a * 12 + b]);
           if (12 * k + a == v) p += alpha;
@@ -535,8 +689,11 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 
   double cscale = 1.0;  // OSQP's cost scaling c
   // column inf-norms of (D P D) WITHOUT the c factor -> vecA   (scaling.c:30-43, lin_alg.c:358)
+  // (code size matters more than ILP here: the kernel's phases compete for the instruction cache,
+  // so the k loop is kept rolled and the lambda has ONE call site)
   auto col_norms_P = [&]() {
     LANES_BEGIN
+#pragma unroll 1
     for (int v = lane; v < NV; v += NL) {
       const int k2 = v / 12, b = v % 12;
       double g1[12], g2[12];
@@ -546,6 +703,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         g2[a] = 2.0 * G2[a * 12 + b];
       }
       double m0 = 0, m1 = 0;
+#pragma unroll 1
       for (int k = 0; k < H; ++k) {
         const double gk = gam[k * H + k2], nk = nnm[k * H + k2];
         const double* dk = Dsm + 12 * k;
@@ -562,65 +720,71 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
     WSYNC();
   };
-  if (prm.scaling_iters > 0) col_norms_P();
-  for (int it = 0; it < prm.scaling_iters; ++it) {
-    // D_temp, E_temp from the current scaled P, A (scaling.c:78-93)
-    LANES_BEGIN
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const int j = lane + NL * s;
-      if (_(valid)[s]) {
-        const double* E = _(Ev)[s];
-        const double* Dd = _(Dv)[s];
-        const double am0 = fabs(mu0), am1 = fabs(mu1), am2 = fabs(mu2), am3 = fabs(mu3);
-        double colA[3];
-        colA[0] = fmax(E[0], E[1]) * Dd[0];
-        colA[1] = fmax(E[2], E[3]) * Dd[1];
-        colA[2] = fmax(fmax(fmax(E[0] * am0, E[1] * am1), fmax(E[2] * am2, E[3] * am3)), E[4]) * Dd[2];
-        double rowA[5];
-        rowA[0] = E[0] * fmax(Dd[0], am0 * Dd[2]);
-        rowA[1] = E[1] * fmax(Dd[0], am1 * Dd[2]);
-        rowA[2] = E[2] * fmax(Dd[1], am2 * Dd[2]);
-        rowA[3] = E[3] * fmax(Dd[1], am3 * Dd[2]);
-        rowA[4] = E[4] * Dd[2];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const double nrm = fmax(cscale * vecA[3 * j + a], colA[a]);
-          const double dtmp = 1.0 / sqrt(limit_scaling(nrm));
-          _(Dv)[s][a] *= dtmp;
-          _(qb)[s][a] *= dtmp;
-          Dsm[3 * j + a] = _(Dv)[s][a];
+  // Ruiz passes: col_norms -> D/E update -> col_norms -> cost normalisation -> D/E update -> ...
+  // written as one loop whose top is the only col_norms_P() call site.
+  if (prm.scaling_iters > 0) {
+    for (int it = 0;; ++it) {
+      col_norms_P();
+      if (it > 0) {
+        // cost normalisation of pass it-1 (scaling.c:117-146)
+        LANES_BEGIN
+        double ssum = 0, qmax = 0;
+        for (int v = lane; v < NV; v += NL) ssum += cscale * vecA[v];
+    #pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (_(valid)[s])
+    #pragma unroll
+            for (int a = 0; a < 3; ++a) qmax = fmax(qmax, fabs(_(qb)[s][a]));
+        _(red) = ssum;
+        _(red2) = qmax;
+        LANES_END
+        {
+          const double mean = WSUM(red) / (double)NV;
+          const double nq = limit_scaling(WMAX(red2));
+          const double ctemp = 1.0 / limit_scaling(fmax(mean, nq));
+          cscale *= ctemp;
+          LANES_BEGIN
+    #pragma unroll
+          for (int s = 0; s < NS; ++s)
+    #pragma unroll
+            for (int a = 0; a < 3; ++a) _(qb)[s][a] *= ctemp;
+          LANES_END
         }
-#pragma unroll
-        for (int r = 0; r < 5; ++r) _(Ev)[s][r] *= 1.0 / sqrt(limit_scaling(rowA[r]));
-      }
-    }
-    LANES_END
-    WSYNC();
-    // cost normalisation (scaling.c:117-146)
-    col_norms_P();
-    LANES_BEGIN
-    double ssum = 0, qmax = 0;
-    for (int v = lane; v < NV; v += NL) ssum += cscale * vecA[v];
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if (_(valid)[s])
-#pragma unroll
-        for (int a = 0; a < 3; ++a) qmax = fmax(qmax, fabs(_(qb)[s][a]));
-    _(red) = ssum;
-    _(red2) = qmax;
-    LANES_END
-    {
-      const double mean = WSUM(red) / (double)NV;
-      const double nq = limit_scaling(WMAX(red2));
-      const double ctemp = 1.0 / limit_scaling(fmax(mean, nq));
-      cscale *= ctemp;
+        }
+      if (it == prm.scaling_iters) break;
+      // D_temp, E_temp from the current scaled P, A (scaling.c:78-93)
       LANES_BEGIN
-#pragma unroll
-      for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) _(qb)[s][a] *= ctemp;
+  #pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int j = lane + NL * s;
+        if (_(valid)[s]) {
+          const double* E = _(Ev)[s];
+          const double* Dd = _(Dv)[s];
+          const double am0 = fabs(mu0), am1 = fabs(mu1), am2 = fabs(mu2), am3 = fabs(mu3);
+          double colA[3];
+          colA[0] = fmax(E[0], E[1]) * Dd[0];
+          colA[1] = fmax(E[2], E[3]) * Dd[1];
+          colA[2] = fmax(fmax(fmax(E[0] * am0, E[1] * am1), fmax(E[2] * am2, E[3] * am3)), E[4]) * Dd[2];
+          double rowA[5];
+          rowA[0] = E[0] * fmax(Dd[0], am0 * Dd[2]);
+          rowA[1] = E[1] * fmax(Dd[0], am1 * Dd[2]);
+          rowA[2] = E[2] * fmax(Dd[1], am2 * Dd[2]);
+          rowA[3] = E[3] * fmax(Dd[1], am3 * Dd[2]);
+          rowA[4] = E[4] * Dd[2];
+  #pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const double nrm = fmax(cscale * vecA[3 * j + a], colA[a]);
+            const double dtmp = 1.0 / sqrt(limit_scaling(nrm));
+            _(Dv)[s][a] *= dtmp;
+            _(qb)[s][a] *= dtmp;
+            Dsm[3 * j + a] = _(Dv)[s][a];
+          }
+  #pragma unroll
+          for (int r = 0; r < 5; ++r) _(Ev)[s][r] *= 1.0 / sqrt(limit_scaling(rowA[r]));
+        }
+      }
       LANES_END
+      WSYNC();
     }
   }
   const double cinv = 1.0 / cscale;
@@ -661,72 +825,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     o[2] = Dd[2] * (mu0 * w0 + mu1 * w1 + mu2 * w2 + mu3 * w3 + w4);
   };
 
-  // dense Cholesky (left-looking) of the leading n x n block held as: strictly-lower triangle in
-  // Wp (row-packed), diagonal in colb[0..n).  On exit Wp holds L (strictly lower), dinv[i] = 1/L_ii.
-  // Row i is owned by lane i % NL; inner loops have warp-uniform trip counts (j).
-  auto cholesky = [&](int n) {
-    // ONE barrier per column: every lane that owns a row below the diagonal recomputes the pivot
-    // d_j = H_jj - sum_k L_jk^2 from the row-j values it loads anyway, so it can scale its own
-    // element without waiting for the owner of row j.  The input diagonal lives in hdiag (= colb,
-    // free until invert_lower) so that writing dinv[j] cannot race with readers of H_jj.
-    double* const hdiag = colb;
-    for (int j = 0; j < n; ++j) {
-      const double* rowj = Wp + tri(j);
-      LANES_BEGIN
-      for (int i = j + ((lane - j) & (NL - 1)); i < n; i += NL) {
-        double* rowi = Wp + tri(i);
-        double a0 = (i == j) ? 0.0 : rowi[j], a1 = 0.0, d0 = hdiag[j], d1 = 0.0;
-        int k = 0;
-#pragma unroll 2
-        for (; k + 1 < j; k += 2) {
-          const double l0 = rowj[k], l1 = rowj[k + 1];
-          a0 -= rowi[k] * l0;
-          a1 -= rowi[k + 1] * l1;
-          d0 -= l0 * l0;
-          d1 -= l1 * l1;
-        }
-        if (k < j) {
-          const double l0 = rowj[k];
-          a0 -= rowi[k] * l0;
-          d0 -= l0 * l0;
-        }
-        const double inv = 1.0 / sqrt(d0 + d1);
-        if (i == j) dinv[j] = inv;
-        else rowi[j] = (a0 + a1) * inv;
-      }
-      LANES_END
-      WSYNC();
-    }
-  };
-
-  // in-place inverse of the lower factor: W = L^-1 (strictly-lower part in Wp, W_ii = dinv[i]).
-  // Column sweep j = n-2 .. 0 of  W[i][j] = -(sum_{k=j+1..i} W[i][k] L[k][j]) / L[j][j]; column j of
-  // L is staged in colb (double buffered) because its owners overwrite it with W.
-  auto invert_lower = [&](int n) {
-    for (int j = n - 2; j >= 0; --j) {
-      double* const buf = colb + (j & 1) * PCAP;
-      LANES_BEGIN
-      for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) buf[i] = Wp[tri(i) + j];
-      LANES_END
-      WSYNC();
-      LANES_BEGIN
-      const double dj = dinv[j];
-      for (int i = j + 1 + ((lane - j - 1) & (NL - 1)); i < n; i += NL) {
-        double* rowi = Wp + tri(i);
-        double a0 = dinv[i] * buf[i], a1 = 0.0;
-        int k = j + 1;
-#pragma unroll 2
-        for (; k + 1 < i; k += 2) {
-          a0 += rowi[k] * buf[k];
-          a1 += rowi[k + 1] * buf[k + 1];
-        }
-        if (k < i) a0 += rowi[k] * buf[k];
-        rowi[j] = -(a0 + a1) * dj;
-      }
-      LANES_END
-    }
-    WSYNC();
-  };
+  constexpr int CB = kFactorBlock;
+  static_assert(PCAP % CB == 0 && NW % CB == 0, "factor sizes must be multiples of the block width");
+  auto cholesky = [&](int n) { cholesky_blocked<PCAP>(Wp, colb, dinv, n MPC_LANE_PASS); };
+  auto invert_lower = [&](int n) { invert_lower_blocked<PCAP>(Wp, dinv, n MPC_LANE_PASS); };
 
   // factor(): Delta^-1 per leg-step, F_k^-1, Hm, Cholesky, W = L^-1 into the upper triangle.
   // wrow = per-row weights are rho_j on every row of a leg-step (ADMM factorisation).
@@ -1400,12 +1502,22 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
       LANES_END
       WSYNC();
-      cholesky(nf);
+      // pad to a multiple of the factorisation's block width with identity rows
+      const int nfp = ((nf + CB - 1) / CB) * CB;
+      LANES_BEGIN
+      for (int f = nf + lane; f < nfp; f += NL) {
+        double* const row = Wp + tri(f);
+        for (int f2 = 0; f2 < f; ++f2) row[f2] = 0.0;
+        colb[f] = 1.0;
+      }
+      LANES_END
+      WSYNC();
+      cholesky(nfp);
       // polish vectors: Dsm is free here (D is also held in registers), colb holds xi_0
       double* const pv = Dsm;        // [nf] right-hand side / solution of the triangular solves
       double* const pxi = Dsm + PCAP;  // [nf] current xi
       double* const pxi0 = colb;     // [nf] first regularised solve (colb is free again after invert_lower)
-      invert_lower(nf);             // W = L^-1: every solve below is two barrier-light mat-vecs
+      invert_lower(nfp);            // W = L^-1: every solve below is two barrier-light mat-vecs
       auto tri_solve = [&]() {      // pv <- W^T (W pv) = (L L^T)^-1 pv
         double* const ty = colb + PCAP;
         LANES_BEGIN

@@ -26,6 +26,11 @@ static_assert(MPC_NL == 32 || MPC_NL == 64, "MPC_NL must be 32 or 64");
 // ------------------------------------------------------------------ device build
 #define MPC_FN __device__ __forceinline__
 #define MPC_LANEFN __device__ __forceinline__
+// a lane program kept out of line (ONE copy in the kernel: instruction-cache footprint); only for
+// rarely-called phases that live entirely in shared memory - a call spills the caller's registers
+#define MPC_NOINLINE_FN __device__ __noinline__
+#define MPC_LANE_ARG , const int lane
+#define MPC_LANE_PASS , lane
 #define LANES_BEGIN {
 #define LANES_END }
 #define PER_LANE(T, name) T name
@@ -114,6 +119,9 @@ struct double2 {
 };
 #define MPC_FN inline
 #define MPC_LANEFN inline
+#define MPC_NOINLINE_FN inline
+#define MPC_LANE_ARG
+#define MPC_LANE_PASS
 #define LANES_BEGIN for (int lane = 0; lane < MPC_NL; ++lane) {
 #define LANES_END }
 #define PER_LANE(T, name) T name[MPC_NL]

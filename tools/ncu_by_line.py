@@ -28,19 +28,33 @@ rows = list(csv.reader(raw.split("\n")))
 hdr = rows[1]
 data = [r for r in rows[2:] if len(r) == len(hdr)]
 ii, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
+STALLS = ["stall_no_inst", "stall_barrier", "stall_short_sb", "stall_long_sb", "stall_mio", "stall_wait", "stall_math"]
+ist = [hdr.index(k) for k in STALLS]
 assert len(seq) == len(data), (len(seq), len(data))
-agg = collections.defaultdict(lambda: [0, 0])
+agg = collections.defaultdict(lambda: [0, 0] + [0] * len(STALLS))
+tot_st = [0] * len(STALLS)
 ti = ts = 0
 for (loc, ins), r in zip(seq, data):
     a, b = int(r[ii]), int(r[isamp])
     agg[loc][0] += a; agg[loc][1] += b; ti += a; ts += b
+    for q, ix in enumerate(ist):
+        v = int(r[ix] or 0); agg[loc][2 + q] += v; tot_st[q] += v
 src = {}
 print(f"SASS instructions {len(seq)}, executed {ti}, samples {ts}")
-for loc, (a, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+print("stall samples: " + ", ".join(f"{k[6:]} {v / ts * 100:.1f}%" for k, v in zip(STALLS, tot_st)))
+# coarse regions (50-line windows of the solver source) by samples
+reg = collections.defaultdict(lambda: [0, 0, 0, 0])
+for loc, v in agg.items():
+    key = (loc[0], loc[1] // 50 * 50) if loc else None
+    reg[key][0] += v[0]; reg[key][1] += v[1]; reg[key][2] += v[2]; reg[key][3] += v[3]
+print("regions (50 source lines): inst% samp% no_inst% barrier%")
+for key, v in sorted(reg.items(), key=lambda kv: -kv[1][1])[:16]:
+    print(f"  {str(key):34s} {v[0] / ti * 100:5.1f} {v[1] / ts * 100:5.1f} {v[2] / ts * 100:5.1f} {v[3] / ts * 100:5.1f}")
+for loc, (a, b, *st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     line = ""
     if loc:
         fn = os.path.join(root, "rl_mpc_locomotion_b200", "csrc", loc[0])
         if os.path.exists(fn):
             src.setdefault(fn, open(fn).read().split("\n"))
             line = src[fn][loc[1] - 1].strip()[:80]
-    print(f"{str(loc):30s} inst {a / ti * 100:5.1f}% samp {b / ts * 100:5.1f}%  {line}")
+    print(f"{str(loc):30s} inst {a / ti * 100:5.1f}% samp {b / ts * 100:5.1f}% noinst {st[0] / ts * 100:4.1f}% bar {st[1] / ts * 100:4.1f}%  {line}")
