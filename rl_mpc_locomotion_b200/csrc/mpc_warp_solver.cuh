@@ -200,27 +200,58 @@ MPC_NOINLINE_FN void cholesky_blocked(double* Wp, double* colb, double* dinv, in
     double* const stage = colb + PCAP;  // [CB(CB+1)/2] updated diagonal block, row-packed with diagonal
     for (int J = 0; J < n; J += CB) {
       const double* const pj = Wp + tri(J);  // row J+c starts at pj + c*J + c(c+1)/2
+      // once at most 32 rows remain, the two warps share each row: CB/2 columns per lane
+      const bool split = (NL == 64) && (n - J <= 32);
       LANES_BEGIN
-      for (int i = lane; i < n; i += NL) {
-        if (i < J) continue;
-        double* const rowi = Wp + tri(i);
-        const int r = i - J;  // < CB: a row of the diagonal block
-        double acc[CB];
+      if (!split) {
+        for (int i = lane; i < n; i += NL) {
+          if (i < J) continue;
+          double* const rowi = Wp + tri(i);
+          const int r = i - J;  // < CB: a row of the diagonal block
+          double acc[CB];
 #pragma unroll
-        for (int c = 0; c < CB; ++c) acc[c] = (c < r) ? rowi[J + c] : (c == r ? hdiag[i] : 0.0);
+          for (int c = 0; c < CB; ++c) acc[c] = (c < r) ? rowi[J + c] : (c == r ? hdiag[i] : 0.0);
 #pragma unroll 2
-        for (int k = 0; k < J; ++k) {
-          const double li = rowi[k];
+          for (int k = 0; k < J; ++k) {
+            const double li = rowi[k];
 #pragma unroll
-          for (int c = 0; c < CB; ++c) acc[c] -= li * pj[c * J + (c * (c + 1)) / 2 + k];
+            for (int c = 0; c < CB; ++c) acc[c] -= li * pj[c * J + (c * (c + 1)) / 2 + k];
+          }
+          if (r < CB) {
+#pragma unroll
+            for (int c = 0; c < CB; ++c)
+              if (c <= r) stage[tri(r) + c] = acc[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < CB; ++c) rowi[J + c] = acc[c];
+          }
         }
-        if (r < CB) {
+      } else {
+        constexpr int CH = CB / 2;
+        const int i = J + (lane & 31), c0 = (lane >> 5) * CH;
+        if (i < n) {
+          double* const rowi = Wp + tri(i);
+          const int r = i - J;
+          double acc[CH];
+          int off[CH];
 #pragma unroll
-          for (int c = 0; c < CB; ++c)
-            if (c <= r) stage[tri(r) + c] = acc[c];
-        } else {
+          for (int q = 0; q < CH; ++q) {
+            const int c = c0 + q;
+            off[q] = c * J + (c * (c + 1)) / 2;
+            acc[q] = (c < r) ? rowi[J + c] : (c == r ? hdiag[i] : 0.0);
+          }
+#pragma unroll 2
+          for (int k = 0; k < J; ++k) {
+            const double li = rowi[k];
 #pragma unroll
-          for (int c = 0; c < CB; ++c) rowi[J + c] = acc[c];
+            for (int q = 0; q < CH; ++q) acc[q] -= li * pj[off[q] + k];
+          }
+#pragma unroll
+          for (int q = 0; q < CH; ++q) {
+            const int c = c0 + q;
+            if (r >= CB) rowi[J + c] = acc[q];
+            else if (c <= r) stage[tri(r) + c] = acc[q];
+          }
         }
       }
       LANES_END
@@ -1228,12 +1259,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     double nr_[14];
-    for (int q = 0; q < 14; ++q) {
-      LANES_BEGIN
-      _(red) = _(nrm)[q];
-      LANES_END
-      nr_[q] = WMAX(red);
-    }
+    WMAXV(nr_, nrm);
     pri_res = nr_[0];
     dua_res = cinv * nr_[1];
     if (!(pri_res <= 1e30) || !(dua_res <= 1e30)) {   // diverged / NaN: OSQP_NON_CVX (auxil.c:697-704)

@@ -46,10 +46,34 @@ namespace mpcw {
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
-// one 8-slot exchange buffer per CTA (one robot per CTA) for the cross-warp hop
+// one exchange buffer per CTA (one robot per CTA) for the cross-warp hop: 8 scalar slots + 2x16
+// for the vector reduction
 __device__ __forceinline__ double* xbuf() {
-  __shared__ double buf[8];
+  __shared__ double buf[8 + 32];
   return buf;
+}
+// K maxima at once: K butterflies, ONE shared-memory hop (2 barriers instead of 2K)
+template <int K>
+__device__ __forceinline__ void wmaxv(const double (&v)[K], double (&out)[K]) {
+  static_assert(K <= 16, "exchange buffer holds 16 values per warp");
+#pragma unroll
+  for (int q = 0; q < K; ++q) {
+    double t = v[q];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) t = fmax(t, shfl_xor_d(t, m));
+    out[q] = t;
+  }
+#if MPC_NL == 64
+  double* b = xbuf() + 8;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < K; ++q) b[(threadIdx.x >> 5) * 16 + q] = out[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < K; ++q) out[q] = fmax(b[q], b[16 + q]);
+  __syncthreads();
+#endif
 }
 __device__ __forceinline__ double wmax(double v) {
 #pragma unroll
@@ -108,6 +132,8 @@ __device__ __forceinline__ int wexscan_i(int v, int lane) {
 #define WMAX(v) mpcw::wmax(v)
 #define WSUM(v) mpcw::wsum(v)
 #define WSUM_I(v) mpcw::wsum_i(v)
+// dst[K] (uniform) = element-wise max over the lanes of the per-lane array src[K]
+#define WMAXV(dst, src) mpcw::wmaxv(src, dst)
 // dst (per-lane int) = exclusive scan of src (per-lane int)
 #define WEXSCAN_I(dst, src) dst = mpcw::wexscan_i(src, lane)
 
@@ -134,6 +160,14 @@ inline double wmax(const double (&v)[MPC_NL]) {
   double m = v[0];
   for (int i = 1; i < MPC_NL; ++i) m = std::fmax(m, v[i]);
   return m;
+}
+template <int K>
+inline void wmaxv(const double (&v)[MPC_NL][K], double (&out)[K]) {
+  for (int q = 0; q < K; ++q) {
+    double m = v[0][q];
+    for (int i = 1; i < MPC_NL; ++i) m = std::fmax(m, v[i][q]);
+    out[q] = m;
+  }
 }
 inline double wsum(const double (&v)[MPC_NL]) {
   // same association order as the device build: a 32-lane butterfly per warp, then warp0+warp1
@@ -167,5 +201,6 @@ inline void wexscan_i(int (&dst)[MPC_NL], const int (&src)[MPC_NL]) {
 #define WMAX(v) mpcw::wmax(v)
 #define WSUM(v) mpcw::wsum(v)
 #define WSUM_I(v) mpcw::wsum_i(v)
+#define WMAXV(dst, src) mpcw::wmaxv(src, dst)
 #define WEXSCAN_I(dst, src) mpcw::wexscan_i(dst, src)
 #endif
