@@ -812,13 +812,13 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   #pragma unroll
           for (int a = 0; a < 3; ++a) {
             const double nrm = fmax(cscale * vecA[3 * j + a], colA[a]);
-            const double dtmp = 1.0 / sqrt(limit_scaling(nrm));
+            const double dtmp = MPC_RSQRT(limit_scaling(nrm));
             _(Dv)[s][a] *= dtmp;
             _(qb)[s][a] *= dtmp;
             Dsm[3 * j + a] = _(Dv)[s][a];
           }
   #pragma unroll
-          for (int r = 0; r < 5; ++r) _(Ev)[s][r] *= 1.0 / sqrt(limit_scaling(rowA[r]));
+          for (int r = 0; r < 5; ++r) _(Ev)[s][r] *= MPC_RSQRT(limit_scaling(rowA[r]));
         }
       }
       LANES_END
@@ -1179,10 +1179,14 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   PER_LANE_ARR(double, Pxv, [NS][3]);
   PER_LANE_ARR(double, nrm, [14]);
   const int max_iter = prm.fixed_iters > 0 ? prm.fixed_iters : prm.max_iter;
+  double rinv_rho = 1.0 / rho, rinv_eq = 1.0 / (kRhoEqFactor * rho);
+  int until_check = prm.check_every;
   for (iter = 1; iter <= max_iter; ++iter) {
     if (need_factor) {
       factor(prm.sigma);
       need_factor = false;
+      rinv_rho = 1.0 / rho;
+      rinv_eq = 1.0 / (kRhoEqFactor * rho);
     }
     LANES_BEGIN  // rhs = sigma x - q + A^T (rho z - y)      (auxil.c:149-162)
 #pragma unroll
@@ -1204,7 +1208,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       if (_(valid)[s]) {
         double zt[5];
         A_mul(_(Ev)[s], _(Dv)[s], _(xt)[s], zt);
-        const double rinv = 1.0 / _(rhoj)[s];
+        const double rinv = (_(rhoj)[s] == rho) ? rinv_rho : rinv_eq;   // 1 / rho_j without the division
 #pragma unroll
         for (int a = 0; a < 3; ++a) _(xv)[s][a] = ar * _(xt)[s][a] + (1.0 - ar) * _(xv)[s][a];
 #pragma unroll
@@ -1218,8 +1222,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
     }
     LANES_END
-    const bool check = prm.fixed_iters > 0 ? (iter == max_iter) : (iter % prm.check_every == 0);
+    // check_termination every check_every iterations (a countdown instead of iter % check_every)
+    const bool check = prm.fixed_iters > 0 ? (iter == max_iter) : (--until_check == 0);
     if (!check) continue;
+    until_check = prm.check_every;
     // ---- residuals (auxil.c:243-362), unscaled norms for termination, scaled for rho
     LANES_BEGIN
 #pragma unroll
