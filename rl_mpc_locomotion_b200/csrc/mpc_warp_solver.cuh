@@ -185,6 +185,10 @@ MPC_LANEFN void inv6spd(const double* a, double* out) {
 // Dense factorisation kernels of the wrench-space / polish systems (shared memory only).
 // ---------------------------------------------------------------------------------------
 constexpr int kFactorBlock = 6;
+#ifndef MPC_FACTOR_UNROLL
+#define MPC_FACTOR_UNROLL 4   // k-loop unrolling of the factorisation dot products (code size vs loads in flight)
+#endif
+constexpr int kFactorUnroll = MPC_FACTOR_UNROLL;
 #if defined(__CUDACC__) && !defined(MPC_EMULATE)
 #define MPC_RSQRT(x) rsqrt(x)
 #else
@@ -218,7 +222,7 @@ MPC_NOINLINE_FN void cholesky_blocked(double* Wp, double* colb, double* dinv, in
           double acc[CB];
 #pragma unroll
           for (int c = 0; c < CB; ++c) acc[c] = (c < r) ? rowi[J + c] : (c == r ? hdiag[i] : 0.0);
-#pragma unroll 2
+#pragma unroll(kFactorUnroll)
           for (int k = 0; k < J; ++k) {
             const double li = rowi[k];
 #pragma unroll
@@ -247,7 +251,7 @@ MPC_NOINLINE_FN void cholesky_blocked(double* Wp, double* colb, double* dinv, in
             off[q] = c * J + (c * (c + 1)) / 2;
             acc[q] = (c < r) ? rowi[J + c] : (c == r ? hdiag[i] : 0.0);
           }
-#pragma unroll 2
+#pragma unroll(kFactorUnroll)
           for (int k = 0; k < J; ++k) {
             const double li = rowi[k];
 #pragma unroll
@@ -327,7 +331,7 @@ MPC_NOINLINE_FN void invert_lower_blocked(double* Wp, const double* dinv, int n 
 #pragma unroll
             for (int c = 0; c < CB; ++c) S[c] = di * rowi[J + c];
             const double* p = Wp + tri(J + CB) + J;  // &L[k][J]
-#pragma unroll 2
+#pragma unroll(kFactorUnroll)
             for (int k = J + CB; k < i; ++k) {
               const double w = rowi[k];
 #pragma unroll

@@ -6,7 +6,7 @@ rep = sys.argv[1]
 H = sys.argv[2] if len(sys.argv) > 2 else "10"
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "rl_mpc_locomotion_b200", "libmpc_b200.so")
+so = os.environ.get("NCU_LIB", os.path.join(root, "rl_mpc_locomotion_b200", "libmpc_b200.so"))
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
