@@ -1013,7 +1013,12 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         a2 += rowi[k + 2] * g23.x;
         a3 += rowi[k + 3] * g23.y;
       }
-      for (; k < i; ++k) a0 += rowi[k] * vg[k];
+      if (k < i) {  // last 1..3 columns as one predicated body (no scalar tail loop)
+        const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+        a0 += rowi[k] * g01.x;
+        if (k + 1 < i) a1 += rowi[k + 1] * g01.y;
+        if (k + 2 < i) a2 += rowi[k + 2] * vg[k + 2];
+      }
       vw[i] = (a0 + a1) + (a2 + a3);
     }
     LANES_END
@@ -1037,9 +1042,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         a3 += p[3 * i + 6] * y23.y;
         p += 4 * i + 10;
       }
-      for (; i < NW; ++i) {
+      if (i < NW) {  // last 1..3 rows, predicated
         a0 += p[0] * vw[i];
-        p += i + 1;
+        if (i + 1 < NW) a1 += p[i + 1] * vw[i + 1];
+        if (i + 2 < NW) a2 += p[2 * i + 3] * vw[i + 2];
       }
       vt[c] = (a0 + a1) + (a2 + a3);
     }
