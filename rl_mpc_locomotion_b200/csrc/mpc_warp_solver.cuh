@@ -111,6 +111,13 @@ MPC_LANEFN double limit_scaling(double v) {  // scaling.c:7-14
   return v > kMaxScaling ? kMaxScaling : v;
 }
 
+// 1/sqrt(x): one MUFU + Newton steps on the device instead of a square root and a division
+#if defined(__CUDACC__) && !defined(MPC_EMULATE)
+#define MPC_RSQRT(x) rsqrt(x)
+#else
+#define MPC_RSQRT(x) (1.0 / std::sqrt(x))
+#endif
+
 // max / clamp without fmax's NaN-quieting sequence (DSETP + 2 selects instead of ~7 instructions);
 // identical results whenever the running value `m` / the bounds are not NaN, which holds at every
 // use (a NaN candidate is dropped exactly as fmax would drop it; a NaN t passes through clampd and
@@ -146,8 +153,7 @@ MPC_LANEFN void inv6spd(const double* a, double* out) {
     double s = a[j * 6 + j];
 #pragma unroll
     for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-    const double d = sqrt(s);
-    const double id = 1.0 / d;
+    const double id = MPC_RSQRT(s);
     L[j][j] = id;  // store the reciprocal on the diagonal
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
@@ -189,11 +195,6 @@ constexpr int kFactorBlock = 6;
 #define MPC_FACTOR_UNROLL 4   // k-loop unrolling of the factorisation dot products (code size vs loads in flight)
 #endif
 constexpr int kFactorUnroll = MPC_FACTOR_UNROLL;
-#if defined(__CUDACC__) && !defined(MPC_EMULATE)
-#define MPC_RSQRT(x) rsqrt(x)
-#else
-#define MPC_RSQRT(x) (1.0 / std::sqrt(x))
-#endif
 
   // Blocked dense Cholesky (left-looking by block columns of width CB) of the leading n x n block,
   // n a multiple of CB, held as: strictly-lower triangle in Wp (row-packed), diagonal in colb[0..n).
@@ -1365,7 +1366,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
             _(act)[s] |= (1 << r) | ((low ? 0 : 1) << (8 + r));
             rows[na][0] = arow[r][0]; rows[na][1] = arow[r][1]; rows[na][2] = arow[r][2];
             bt[na] = low ? lo : hi;
-            rmax = fmax(rmax, sqrt(arow[r][0] * arow[r][0] + arow[r][1] * arow[r][1] + arow[r][2] * arow[r][2]));
+            rmax = maxd(rmax, arow[r][0] * arow[r][0] + arow[r][1] * arow[r][1] + arow[r][2] * arow[r][2]);  // squared
             ++na;
           }
         }
@@ -1378,9 +1379,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
             const double d = v[0] * Yr[p][0] + v[1] * Yr[p][1] + v[2] * Yr[p][2];
             v[0] -= d * Yr[p][0]; v[1] -= d * Yr[p][1]; v[2] -= d * Yr[p][2];
           }
-          const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-          if (nv > 1e-9 * rmax) {
-            Yr[rank][0] = v[0] / nv; Yr[rank][1] = v[1] / nv; Yr[rank][2] = v[2] / nv;
+          const double nv2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+          if (nv2 > 1e-18 * rmax) {   // |v| > 1e-9 * max row norm
+            const double inv = MPC_RSQRT(nv2);
+            Yr[rank][0] = v[0] * inv; Yr[rank][1] = v[1] * inv; Yr[rank][2] = v[2] * inv;
             ++rank;
           }
         }
@@ -1395,8 +1397,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
           double e[3] = {0, 0, 0};
           e[ax] = 1.0;
           double n1[3] = {y[1] * e[2] - y[2] * e[1], y[2] * e[0] - y[0] * e[2], y[0] * e[1] - y[1] * e[0]};
-          const double l1 = sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
-          n1[0] /= l1; n1[1] /= l1; n1[2] /= l1;
+          const double l1 = MPC_RSQRT(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+          n1[0] *= l1; n1[1] *= l1; n1[2] *= l1;
           const double n2[3] = {y[1] * n1[2] - y[2] * n1[1], y[2] * n1[0] - y[0] * n1[2], y[0] * n1[1] - y[1] * n1[0]};
 #pragma unroll
           for (int a = 0; a < 3; ++a) { _(Yb)[s][0][a] = y[a]; _(Yb)[s][1][a] = n1[a]; _(Yb)[s][2][a] = n2[a]; }
