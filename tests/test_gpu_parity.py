@@ -166,3 +166,50 @@ def test_launch_order_hint_does_not_change_results():
     b = mpc.solve(d_rec, d_rt, full=True, info=True, order=order)
     torch.cuda.synchronize()
     assert torch.equal(a["grf_full"], b["grf_full"]) and torch.equal(a["status"], b["status"])
+
+
+def test_full_size_batch_properties(oracle_mod):
+    """BASELINE config 2 at full size (4096 robots, horizon 10) through size-independent
+    properties: every QP solved, bit-exact determinism, batch/permutation independence (a
+    robot's answer does not depend on its neighbours or its slot), friction-pyramid feasibility,
+    and the oracle on a random sample."""
+    import torch
+    from rl_mpc_locomotion_b200 import synth
+    from rl_mpc_locomotion_b200.batched import BatchedConvexMpc
+    from rl_mpc_locomotion_b200 import records as R
+    n, h = 4096, 10
+    rec, rt, params, _ = synth.make_batch(n, h, seed=11)
+    mpc = BatchedConvexMpc(h, device="cuda:0", robot_params=params)
+    d_rec, d_rt = torch.from_numpy(rec).cuda(), torch.from_numpy(rt).cuda()
+    a = mpc.solve(d_rec, d_rt, full=True)
+    b = mpc.solve(d_rec, d_rt, full=True)
+    assert (a["status"] == 1).all()
+    assert torch.equal(a["grf_full"], b["grf_full"])
+    rng = np.random.default_rng(0)
+    perm = torch.from_numpy(rng.permutation(n)).cuda()
+    c = mpc.solve(d_rec[perm].contiguous(), d_rt[perm].contiguous(), full=True)
+    assert torch.equal(c["grf_full"], a["grf_full"][perm])
+    sub = torch.from_numpy(np.sort(rng.choice(n, 100, replace=False))).cuda()
+    d = mpc.solve(d_rec[sub].contiguous(), d_rt[sub].contiguous(), full=True)
+    assert torch.equal(d["grf_full"], a["grf_full"][sub])
+    # friction pyramid (mpc_osqp.cc:440-470, rows indexed the reference's way: row r uses
+    # foot_friction_coeffs[r]) on x = -output.  OSQP stops at a primal residual of
+    # eps_abs + eps_rel * max(|Ax|, |z|) with eps = 1e-3, so the returned iterate may violate a
+    # row by that much (the reference's own output does: up to 0.5 N on this distribution);
+    # swing legs are equality rows (0 <= A x <= 0).
+    f = -a["grf_full"].cpu().numpy().astype(np.float64).reshape(n, h, 4, 3)
+    contact = rec[:, R.REC_CONTACT:R.REC_CONTACT + 4 * h].reshape(n, h, 4)
+    mu = rec[:, R.REC_MU:R.REC_MU + 4].astype(np.float64)[:, None, None, :]      # [n,1,1,row]
+    fx, fy, fz = f[..., 0], f[..., 1], f[..., 2]
+    rows = np.stack([-fx + mu[..., 0] * fz, fx + mu[..., 1] * fz, -fy + mu[..., 2] * fz, fy + mu[..., 3] * fz, fz], -1)
+    stance = (contact > 0)[..., None]
+    viol = np.where(stance, np.maximum(-rows, 0.0), np.abs(rows)).reshape(n, -1).max(axis=1)
+    scale = np.abs(rows).reshape(n, -1).max(axis=1)
+    assert (viol <= 1.5 * (1e-3 + 1e-3 * scale)).all()
+    fz_max = (params[rt, 0].astype(np.float64) * 9.8 * 10.0)[:, None, None]
+    assert (fz <= fz_max + 1.0).all()
+    # the oracle on a random sample of the same batch
+    idx = np.sort(rng.choice(n, 96, replace=False))
+    ref0, _, st_ref = oracle_mod.solve_records(rec[idx], h, params, rt[idx], mode=oracle_mod.COLD, full=True)
+    assert (st_ref == 1).all()
+    assert np.abs(a["grf0"].cpu().numpy()[idx] - ref0).max() < TOL_N
