@@ -213,6 +213,8 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
 #define MPC_ST_NORMAL     87   /* [3]  ground normal (yaw frame)                */
 #define MPC_ST_UNSAFE     90   /* int  locomotionSafe() == False this tick (FSM_State_Locomotion.py:104-136);
                                         only evaluated when d_body is given                */
+#define MPC_ST_ITERS      91   /* int  OSQP iterations of this robot's last MPC solve (scheduling hint for
+                                        d_order, see mpc_b200_tick)                        */
 #define MPC_TICK_STATE_STRIDE 96
 
 typedef struct MpcB200TickParams {
@@ -239,13 +241,18 @@ typedef struct MpcB200TickParams {
  *   d_records[n, MPC_REC_STRIDE(h)] float32 out or NULL: the QP record built this tick (tests)
  *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise
  *   d_warm   [n, MPC_WARM_STRIDE(h)] float64 in/out or NULL: see mpc_b200_solve_batch
+ *   d_order  [n] int32 or NULL: launch order (CTA b runs robot d_order[b]), a pure scheduling
+ *            hint as in mpc_b200_solve_batch; consecutive MPC solves of a robot need similar
+ *            iteration counts, so sorting the robots by descending MPC_ST_ITERS of the previous
+ *            MPC tick shortens the tail of the launch
  */
 int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick,
                   const float* d_dof, const float* d_body, const float* d_est, const float* d_cmd,
                   int has_weights,
                   const int32_t* d_gait, const float* d_robot_params, const float* d_robot_geom,
                   const int32_t* d_robot_type, int n_robots, float* d_state, float* d_torques,
-                  float* d_grf0, float* d_records, int32_t* d_solved, double* d_warm, void* stream);
+                  float* d_grf0, float* d_records, int32_t* d_solved, double* d_warm,
+                  const int32_t* d_order, void* stream);
 
 /* Debug / test hook: run ONE record through the solve kernel and copy back the
  * quantities the kernel never materialises in production: the dense Hessian

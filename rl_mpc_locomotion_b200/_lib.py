@@ -66,7 +66,7 @@ def lib():
         L.mpc_b200_debug_build_qp.argtypes = [C.POINTER(Settings), vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_debug_build_qp.restype = C.c_int
         L.mpc_b200_tick.argtypes = [C.POINTER(Settings), C.POINTER(TickParams), vp, vp, vp, vp, C.c_int, vp, vp, vp,
-                                    vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+                                    vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tick.restype = C.c_int
         _lib = L
     return _lib

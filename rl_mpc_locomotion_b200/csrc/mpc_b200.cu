@@ -144,7 +144,8 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
                 const int32_t* __restrict__ gait, const float* __restrict__ robot_params,
                 const float* __restrict__ robot_geom, const int32_t* __restrict__ robot_type, int n_robots,
                 float* __restrict__ state, float* __restrict__ torques, float* __restrict__ grf0,
-                float* __restrict__ records, int32_t* __restrict__ solved, double* __restrict__ warm) {
+                float* __restrict__ records, int32_t* __restrict__ solved, double* __restrict__ warm,
+                const int32_t* __restrict__ order) {
   using K = KernelCfg<H>;
   using T = TickCfg<H>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,8 +161,8 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
   float* grf_s = geom_s + 24;
   int32_t* stat_s = reinterpret_cast<int32_t*>(grf_s + 12);
   const int lane = threadIdx.x;
-  const int robot = blockIdx.x;
-  if (robot >= n_robots) return;
+  if ((int)blockIdx.x >= n_robots) return;
+  const int robot = order ? order[blockIdx.x] : (int)blockIdx.x;   // scheduling hint only
   const int type = robot_type ? robot_type[robot] : 0;
   for (int i = lane; i < MPC_TICK_STATE_STRIDE; i += MPC_NL) st_s[i] = state[(size_t)robot * MPC_TICK_STATE_STRIDE + i];
   if (lane < 24) {
@@ -190,9 +191,11 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) records[(size_t)robot * K::REC_FLOATS + i] = rec_s[i];
   if (do_solve) {
     mpc::fill_tables<H>(sm, prm.dt, lane);
-    mpc::solve_robot<H, WARM>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, nullptr, nullptr,
+    __shared__ double info_s[mpc::INFO_STRIDE];
+    mpc::solve_robot<H, WARM>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, info_s, nullptr,
                               warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
     __syncthreads();
+    if (lane == 0) reinterpret_cast<int*>(st_s)[MPC_ST_ITERS] = (int)info_s[mpc::INFO_ITERS];
     if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
   }
   mpc::tick_post(est_s, geom_s, do_solve ? grf_s : nullptr, st_s, legs_s, torques + (size_t)robot * 12, lane);
@@ -204,7 +207,7 @@ template <int H>
 int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* body,
                 const float* est, const float* cmd, int has_weights, const int32_t* gait, const float* rp, const float* geom,
                 const int32_t* rt, int n, float* state, float* torques, float* grf0, float* records,
-                int32_t* solved, double* warm, cudaStream_t stream) {
+                int32_t* solved, double* warm, const int32_t* order, cudaStream_t stream) {
   using T = TickCfg<H>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -217,10 +220,12 @@ int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const fl
   if (n <= 0) return MPC_B200_OK;
   if (warm)
     mpc_tick_kernel<H, true><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp,
-                                                                  geom, rt, n, state, torques, grf0, records, solved, warm);
+                                                                  geom, rt, n, state, torques, grf0, records, solved, warm,
+                                                                  order);
   else
     mpc_tick_kernel<H, false><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp,
-                                                                   geom, rt, n, state, torques, grf0, records, solved, nullptr);
+                                                                   geom, rt, n, state, torques, grf0, records, solved, nullptr,
+                                                                   order);
   CK(cudaGetLastError());
   return MPC_B200_OK;
 }
@@ -469,7 +474,7 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
                   const int32_t* d_gait,
                   const float* d_robot_params, const float* d_robot_geom, const int32_t* d_robot_type,
                   int n_robots, float* d_state, float* d_torques, float* d_grf0, float* d_records,
-                  int32_t* d_solved, double* d_warm, void* stream) {
+                  int32_t* d_solved, double* d_warm, const int32_t* d_order, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
   if (!tick || tick->iters_between_mpc <= 0 || !(tick->dt > 0)) {
@@ -498,9 +503,9 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
   cudaStream_t st = (cudaStream_t)stream;
   if (settings->horizon == 10)
     return launch_tick<10>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
-                           d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, st);
+                           d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, d_order, st);
   return launch_tick<16>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
-                         d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, st);
+                         d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, d_order, st);
 }
 
 int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_record,

@@ -23,7 +23,8 @@ from .robots import TICK_STATE_STRIDE, geom_table, initial_tick_state, params_ta
 
 class BatchedLocomotion:
     def __init__(self, robot_type, gait, horizon: int = 10, device="cuda", dt: float = 0.01,
-                 iters_between_mpc: int = 2, flat_ground: bool = False, warm_start: bool = False, **settings):
+                 iters_between_mpc: int = 2, flat_ground: bool = False, warm_start: bool = False,
+                 longest_first: bool = True, **settings):
         """``robot_type`` / ``gait``: per-robot int arrays (RobotType values; gait ids as in
         ConvexMPCLocomotion.run :227-241 — the reference can only express ONE global gait,
         Parameters.cmpc_gait)."""
@@ -48,6 +49,9 @@ class BatchedLocomotion:
         # ConvexMpc object and warm-starts every tick (mpc_osqp.cc:757-778); off by default
         # (cold start = the golden-vector semantics)
         self.warm = torch.zeros((self.n, 2 + 76 * horizon), dtype=torch.float64, device=dev) if warm_start else None
+        self.longest_first = bool(longest_first) and self.n > 1
+        self.order = None           # int32 [N] launch order for the next tick, or None (index order)
+        self._ticks = 0             # the kernel's iterationCounter of robots that were never reset
 
     @property
     def unsafe(self) -> torch.Tensor:
@@ -62,6 +66,7 @@ class BatchedLocomotion:
         so the OSQP workspace state is dropped too."""
         if idx is None:
             self.state.copy_(self._fresh)
+            self.order = None
             if self.warm is not None:
                 self.warm.zero_()
         else:
@@ -88,6 +93,11 @@ class BatchedLocomotion:
                                           p(root_states), p(est), p(commands), int(has_weights), p(self.gait), p(self.robot_params),
                                           p(self.robot_geom), p(self.robot_type), self.n, p(self.state),
                                           p(self.torques), p(self.grf0), p(records_out), p(self.solved),
-                                          p(self.warm), C.c_void_p(stream))
+                                          p(self.warm), p(self.order), C.c_void_p(stream))
         _lib.check(rc, "mpc_b200_tick")
+        if self.longest_first and self._ticks % self.tick_params.iters_between_mpc == 0:
+            # this was (for robots never reset individually) an MPC tick: sort for the next one
+            iters = self.state.view(torch.int32)[:, 91]          # MPC_ST_ITERS
+            self.order = torch.argsort(iters, descending=True, stable=True).to(torch.int32)
+        self._ticks += 1
         return self.torques

@@ -63,6 +63,10 @@ def test_batched_tick_equals_single_robot_ticks():
         tau = big.run(torch.from_numpy(dof).cuda(), None, torch.from_numpy(cmd).cuda(), has_weights=False,
                       est=torch.from_numpy(est).cuda()).cpu().numpy().copy()
         outs.append((dof, est, cmd, tau))
+    # the launch-order hint (longest OSQP solve first) was active from the second MPC tick on
+    iters = big.state.view(torch.int32)[:, 91].cpu().numpy()          # MPC_ST_ITERS
+    assert big.order is not None and sorted(big.order.cpu().tolist()) == list(range(n))
+    assert (iters >= 25).all() and (iters <= 4000).all()
     for r in (0, 17, 95):
         one = BatchedLocomotion([rtype[r]], [gait[r]], device="cuda:0")
         for dof, est, cmd, tau in outs:

@@ -79,8 +79,10 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     if (records) std::memcpy(records + (size_t)r * stride, rec, sizeof(rec));
     if (do_solve) {
       mpc::fill_tables<H>(sm.data(), prm.dt);
+      double info[mpc::INFO_STRIDE] = {0};
       mpc::solve_robot<H, true>(rec, rp + (size_t)type * MPC_ROBOT_PARAMS_STRIDE, prm, sm.data(), grf, nullptr, &st_code,
-                          nullptr, nullptr, nullptr, warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+                          nullptr, info, nullptr, warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+      reinterpret_cast<int*>(st)[MPC_ST_ITERS] = (int)info[mpc::INFO_ITERS];
       if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
     }
     mpc::tick_post(e, g, do_solve ? grf : nullptr, st, legs, torques + (size_t)r * 12);

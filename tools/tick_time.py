@@ -8,7 +8,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 warm = len(sys.argv) > 2 and sys.argv[2] == "warm"
 rng = np.random.default_rng(0)
 gait = rng.choice([0, 6, 1], n)
-loco = BatchedLocomotion(np.zeros(n, np.int32), gait, device="cuda:0", warm_start=warm)
+lf = not (len(sys.argv) > 3 and sys.argv[3] == "nolf")
+loco = BatchedLocomotion(np.zeros(n, np.int32), gait, device="cuda:0", warm_start=warm, longest_first=lf)
 stand = np.tile([0.0, 0.8, -1.6], 4)
 
 
@@ -37,5 +38,5 @@ for i in range(40):
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(40)]
 mpc_ms, plain_ms = np.mean(sorted(ms)[20:]), np.mean(sorted(ms)[:20])
-print(f"n={n} warm_start={warm}: MPC ticks {mpc_ms:.3f} ms, non-MPC ticks {plain_ms:.3f} ms -> {n * 40 / sum(ms) * 1e3:.3e} robot-ticks/s "
+print(f"n={n} warm_start={warm} longest_first={lf}: MPC ticks {mpc_ms:.3f} ms, non-MPC ticks {plain_ms:.3f} ms -> {n * 40 / sum(ms) * 1e3:.3e} robot-ticks/s "
       f"({n / mpc_ms * 1e3:.3e} QP solves/s on MPC ticks); solved {int((loco.solved == 1).sum())}/{n}")
