@@ -24,7 +24,7 @@ from .robots import TICK_STATE_STRIDE, geom_table, initial_tick_state, params_ta
 class BatchedLocomotion:
     def __init__(self, robot_type, gait, horizon: int = 10, device="cuda", dt: float = 0.01,
                  iters_between_mpc: int = 2, flat_ground: bool = False, warm_start: bool = False,
-                 longest_first: bool = True, **settings):
+                 longest_first: bool = False, **settings):
         """``robot_type`` / ``gait``: per-robot int arrays (RobotType values; gait ids as in
         ConvexMPCLocomotion.run :227-241 — the reference can only express ONE global gait,
         Parameters.cmpc_gait)."""

@@ -49,7 +49,7 @@ def test_batched_tick_equals_single_robot_ticks():
     n = 96
     rtype = rng.integers(0, 3, n)
     gait = rng.choice([0, 6, 1], n)
-    big = BatchedLocomotion(rtype, gait, device="cuda:0")
+    big = BatchedLocomotion(rtype, gait, device="cuda:0", longest_first=True)
     stand = np.tile([0.0, 0.8, -1.6], 4)
     outs = []
     for t in range(6):

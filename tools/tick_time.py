@@ -8,7 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 warm = len(sys.argv) > 2 and sys.argv[2] == "warm"
 rng = np.random.default_rng(0)
 gait = rng.choice([0, 6, 1], n)
-lf = not (len(sys.argv) > 3 and sys.argv[3] == "nolf")
+lf = len(sys.argv) > 3 and sys.argv[3] == "lf"
 loco = BatchedLocomotion(np.zeros(n, np.int32), gait, device="cuda:0", warm_start=warm, longest_first=lf)
 stand = np.tile([0.0, 0.8, -1.6], 4)
 
