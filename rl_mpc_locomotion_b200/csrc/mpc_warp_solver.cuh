@@ -1024,29 +1024,23 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
-    LANES_BEGIN  // w = W^T y (column walk: W[i][c] contiguous across lanes for a fixed row i)
+    LANES_BEGIN  // w = W^T y (column walk).  All lanes of a warp visit the SAME row i at the same
+    // time (lanes whose column is not yet below the diagonal are predicated off): W[i][c] is then
+    // contiguous across the lanes (no bank conflicts) and y[i] is a broadcast.  A warp issues its
+    // longest column's trip count anyway, so the uniform loop costs no extra steps.
+    static_assert(NW % 4 == 0, "column walk takes rows four at a time");
     for (int c = lane; c < NW; c += NL) {
       double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int i = c + 1;
-      const double* p = Wp + tri(i) + c;     // &W[i][c]; W[i+1][c] = p[i+1]
-      if ((i & 1) && i < NW) {               // align i to even so that vw pairs are 16-byte aligned
-        a0 += p[0] * vw[i];
-        p += i + 1;
-        ++i;
-      }
-      for (; i + 3 < NW; i += 4) {
+      int i = c & ~31;                       // first column of this warp: a multiple of 4
+      const double* p = Wp + tri(i) + c;     // &W[i][c] (dereferenced only where c < i)
+      for (; i < NW; i += 4) {
         const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
         const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
-        a0 += p[0] * y01.x;
-        a1 += p[i + 1] * y01.y;
-        a2 += p[2 * i + 3] * y23.x;
-        a3 += p[3 * i + 6] * y23.y;
+        if (c < i) a0 += p[0] * y01.x;
+        if (c < i + 1) a1 += p[i + 1] * y01.y;
+        if (c < i + 2) a2 += p[2 * i + 3] * y23.x;
+        if (c < i + 3) a3 += p[3 * i + 6] * y23.y;
         p += 4 * i + 10;
-      }
-      if (i < NW) {  // last 1..3 rows, predicated
-        a0 += p[0] * vw[i];
-        if (i + 1 < NW) a1 += p[i + 1] * vw[i + 1];
-        if (i + 2 < NW) a2 += p[2 * i + 3] * vw[i + 2];
       }
       vt[c] = (a0 + a1) + (a2 + a3);
     }
