@@ -90,8 +90,10 @@ struct Dims {
   static constexpr int OFF_COL = OFF_DINV + PCAP;        // [2][PCAP] column staging (inversion, polish)
   static constexpr int OFF_GAM = OFF_COL + 2 * PCAP;     // [H][H]
   static constexpr int OFF_NN = OFF_GAM + H * H;         // [H][H]
-  static constexpr int OFF_WB = OFF_NN + H * H;          // [6][12] balanced wrench map
-  static constexpr int OFF_Q1S = OFF_WB + 72;            // [6][6] Q1'
+  static constexpr int WBS = 13;                         // row stride of Wb: odd, so the six rows read
+                                                         // by the lanes of a step sit in distinct banks
+  static constexpr int OFF_WB = OFF_NN + H * H;          // [6][WBS] balanced wrench map (12 used per row)
+  static constexpr int OFF_Q1S = OFF_WB + 6 * WBS + (6 * WBS & 1);  // [6][6] Q1'
   static constexpr int OFF_Q2S = OFF_Q1S + 36;           // [6] diag of Q2' (+2 pad)
   static constexpr int OFF_DSM = OFF_Q2S + 8;            // [max(NV, 2 PCAP)] D (scaling); polish vectors
   static constexpr int SMEM_DOUBLES = OFF_DSM + (NV > 2 * PCAP ? NV : 2 * PCAP);
@@ -438,6 +440,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   const double* const gam = sm + D::OFF_GAM;
   const double* const nnm = sm + D::OFF_NN;
   double* const Wb = sm + D::OFF_WB;
+  constexpr int WBS = D::WBS;
   double* const Dsm = sm + D::OFF_DSM;
 
   const double dt = prm.dt, alpha = prm.alpha;
@@ -578,7 +581,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
     for (int c = 0; c < 6; ++c)
 #pragma unroll
-      for (int b = 0; b < 3; ++b) Wb[c * 12 + 3 * leg + b] = _(wbl)[c][b];
+      for (int b = 0; b < 3; ++b) Wb[c * WBS + 3 * leg + b] = _(wbl)[c][b];
   }
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
@@ -655,7 +658,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     for (int a = 0; a < 3; ++a) {
       double q = 0;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) q += Wb[c * 12 + 3 * (lane & 3) + a] * vt[6 * k + c];
+      for (int c = 0; c < 6; ++c) q += Wb[c * WBS + 3 * (lane & 3) + a] * vt[6 * k + c];
       const double qn = _(valid)[s] ? 2.0 * q : 0.0;
       _(qb)[s][a] = qn;
       if (dbg_out && _(valid)[s]) dbg_out[3 * j + a] = qn;   // unscaled q for builder tests
@@ -692,9 +695,9 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     double y1 = 0;
     if (c < 3) {
 #pragma unroll
-      for (int c2 = 0; c2 < 3; ++c2) y1 += Q1at(c, c2) * Wb[c2 * 12 + b];
+      for (int c2 = 0; c2 < 3; ++c2) y1 += Q1at(c, c2) * Wb[c2 * WBS + b];
     } else {
-      y1 = q1p[c - 3] * Wb[c * 12 + b];
+      y1 = q1p[c - 3] * Wb[c * WBS + b];
     }
     Y1[e] = y1;
   }
@@ -706,8 +709,8 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     double g1 = 0, g2 = 0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      g1 += Wb[c * 12 + a] * Y1[c * 12 + b];
-      g2 += Wb[c * 12 + a] * q2d[c] * Wb[c * 12 + b];
+      g1 += Wb[c * WBS + a] * Y1[c * 12 + b];
+      g2 += Wb[c * WBS + a] * q2d[c] * Wb[c * WBS + b];
     }
     G1[e] = g1;
     G2[e] = g2;
@@ -902,7 +905,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
 #pragma unroll
-          for (int a = 0; a < 3; ++a) X[c][a] = Wb[c * 12 + 3 * (lane & 3) + a] * Dd[a];
+          for (int a = 0; a < 3; ++a) X[c][a] = Wb[c * WBS + 3 * (lane & 3) + a] * Dd[a];
           mul3sym(_(di)[s], X[c], Y[c]);
         }
         int e = 0;
@@ -986,7 +989,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       const int k = i / 6, c = i % 6;
       double t = 0;
 #pragma unroll
-      for (int b = 0; b < 12; ++b) t += Wb[c * 12 + b] * vecA[12 * k + b];
+      for (int b = 0; b < 12; ++b) t += Wb[c * WBS + b] * vecA[12 * k + b];
       vt[i] = t;
     }
     LANES_END
@@ -1067,7 +1070,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int a = 0; a < 3; ++a) {
           double t = 0;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) t += Wb[c * 12 + 3 * (lane & 3) + a] * vecB[6 * k + c];
+          for (int c = 0; c < 6; ++c) t += Wb[c * WBS + 3 * (lane & 3) + a] * vecB[6 * k + c];
           u[a] = _(Dv)[s][a] * t;
         }
         mul3sym(_(di)[s], u, du);
@@ -1096,7 +1099,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       const int k = i / 6, c = i % 6;
       double t = 0;
 #pragma unroll
-      for (int b = 0; b < 12; ++b) t += Wb[c * 12 + b] * vecA[12 * k + b];
+      for (int b = 0; b < 12; ++b) t += Wb[c * WBS + b] * vecA[12 * k + b];
       vt[i] = t;
     }
     LANES_END
@@ -1131,7 +1134,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int a = 0; a < 3; ++a) {
           double t = 0;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) t += Wb[c * 12 + 3 * (lane & 3) + a] * vecB[6 * k + c];
+          for (int c = 0; c < 6; ++c) t += Wb[c * WBS + 3 * (lane & 3) + a] * vecB[6 * k + c];
           const double d = _(Dv)[s][a];
           _(xt)[s][a] = cscale * alpha * d * d * _(tmp3)[s][a] + d * t;
         }
@@ -1488,7 +1491,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
             for (int c = 0; c < 6; ++c) {
               m[c] = 0;
 #pragma unroll
-              for (int a = 0; a < 3; ++a) m[c] += Wb[c * 12 + 3 * (lane & 3) + a] * _(Dv)[s][a] * nu[a];
+              for (int a = 0; a < 3; ++a) m[c] += Wb[c * WBS + 3 * (lane & 3) + a] * _(Dv)[s][a] * nu[a];
               Mf[6 * f + c] = m[c];
             }
 #pragma unroll
