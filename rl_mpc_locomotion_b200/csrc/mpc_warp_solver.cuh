@@ -96,7 +96,12 @@ struct Dims {
   static constexpr int OFF_Q1S = OFF_WB + 6 * WBS + (6 * WBS & 1);  // [6][6] Q1'
   static constexpr int OFF_Q2S = OFF_Q1S + 36;           // [6] diag of Q2' (+2 pad)
   static constexpr int OFF_DSM = OFF_Q2S + 8;            // [max(NV, 2 PCAP)] D (scaling); polish vectors
-  static constexpr int SMEM_DOUBLES = OFF_DSM + (NV > 2 * PCAP ? NV : 2 * PCAP);
+  // G_k = F_k^-1 U_k ([NW][GS], GS odd: conflict-free rows) lets ksolve() go from s to g = F^-1 U s
+  // in one stage.  Only where the extra 6.2 KB do not cost a resident CTA (h = 10: still 6 per SM).
+  static constexpr bool FUSE_G = (H <= 10);
+  static constexpr int GS = 13;
+  static constexpr int OFF_G = OFF_DSM + (NV > 2 * PCAP ? NV : 2 * PCAP);
+  static constexpr int SMEM_DOUBLES = OFF_G + (FUSE_G ? NW * GS + (NW * GS & 1) : 0);
   static_assert(SCR_POLISH <= SCR_SIZE, "polish scratch does not fit");
   static_assert(NLS * 21 <= NTRI && 288 + 72 <= NTRI, "staging does not fit in the triangle buffer");
 };
@@ -946,6 +951,16 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_BEGIN
     for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
+      if constexpr (D::FUSE_G) {  // row (k, c) of G = F_k^-1 U
+        double* const grow = sm + D::OFF_G + i * D::GS;
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+          double g = 0;
+#pragma unroll
+          for (int c2 = 0; c2 < 6; ++c2) g += Finv[k * 36 + c * 6 + c2] * Wb[c2 * WBS + b];
+          grow[b] = g;
+        }
+      }
       double* const row = Wp + tri(i);
       const double* q1r = q1s + c * 6;
       for (int k2 = 0; k2 <= k; ++k2) {
@@ -984,26 +999,43 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
-    LANES_BEGIN  // t = U s
-    for (int i = lane; i < NW; i += NL) {
-      const int k = i / 6, c = i % 6;
-      double t = 0;
+    if constexpr (D::FUSE_G) {
+      LANES_BEGIN  // g = (F^-1 U) s in one stage
+      for (int i = lane; i < NW; i += NL) {
+        const int k = i / 6;
+        const double* const grow = sm + D::OFF_G + i * D::GS;
+        double g0 = 0, g1 = 0;
 #pragma unroll
-      for (int b = 0; b < 12; ++b) t += Wb[c * WBS + b] * vecA[12 * k + b];
-      vt[i] = t;
-    }
-    LANES_END
-    WSYNC();
-    LANES_BEGIN  // g = F^-1 t
-    for (int i = lane; i < NW; i += NL) {
-      const int k = i / 6, c = i % 6;
-      double g = 0;
+        for (int b = 0; b < 12; b += 2) {
+          g0 += grow[b] * vecA[12 * k + b];
+          g1 += grow[b + 1] * vecA[12 * k + b + 1];
+        }
+        vg[i] = g0 + g1;
+      }
+      LANES_END
+      WSYNC();
+    } else {
+      LANES_BEGIN  // t = U s
+      for (int i = lane; i < NW; i += NL) {
+        const int k = i / 6, c = i % 6;
+        double t = 0;
 #pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2) g += Finv[k * 36 + c * 6 + c2] * vt[6 * k + c2];
-      vg[i] = g;
+        for (int b = 0; b < 12; ++b) t += Wb[c * WBS + b] * vecA[12 * k + b];
+        vt[i] = t;
+      }
+      LANES_END
+      WSYNC();
+      LANES_BEGIN  // g = F^-1 t
+      for (int i = lane; i < NW; i += NL) {
+        const int k = i / 6, c = i % 6;
+        double g = 0;
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2) g += Finv[k * 36 + c * 6 + c2] * vt[6 * k + c2];
+        vg[i] = g;
+      }
+      LANES_END
+      WSYNC();
     }
-    LANES_END
-    WSYNC();
     LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
     for (int i = lane; i < NW; i += NL) {
       const double* rowi = Wp + tri(i);
