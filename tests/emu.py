@@ -114,3 +114,13 @@ def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robo
                             P(warm.ctypes.data) if warm is not None else None)
     assert rc == 0
     return dict(torques=torques, grf0=grf0, records=records, solved=solved)
+
+
+def chol_inv(A: np.ndarray, pcap: int = 60) -> np.ndarray:
+    """W = chol(A)^-1 through the kernel's blocked Cholesky + triangular inverse lane programs."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    W = np.zeros((n, n))
+    rc = lib().mpc_emu_chol_inv(A.ctypes.data_as(C.c_void_p), n, pcap, W.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return W

@@ -127,3 +127,16 @@ def test_non_finite_input_is_reported_not_propagated():
     assert out["status"][0] == 1 and out["status"][2] == 1
     assert out["status"][1] == -7 and np.all(out["grf_full"][1] == 0)
     assert np.isfinite(out["grf_full"]).all()
+
+
+@pytest.mark.parametrize("n,pcap", [(6, 60), (12, 60), (30, 60), (36, 60), (60, 60), (66, 120), (96, 120), (120, 120)])
+def test_blocked_cholesky_and_inverse_lane_programs(n, pcap):
+    """The two out-of-line factorisation routines on their own (block width 6, column-split mode
+    once <= 32 rows remain, several rows per lane beyond 64 rows) against numpy."""
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n))
+    A = B @ B.T + n * np.eye(n) * rng.uniform(0.5, 2.0)
+    W = emu.chol_inv(A, pcap)
+    Wref = np.linalg.inv(np.linalg.cholesky(A))
+    assert np.abs(W - Wref).max() < 1e-12 * np.abs(Wref).max() * n
+    assert np.abs(W.T @ W @ A - np.eye(n)).max() < 1e-10

@@ -94,3 +94,26 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
 extern "C" void mpc_emu_estimator(const float* body, const float* normal, float* est, int n) {
   for (int r = 0; r < n; ++r) mpc::estimator_update(body + 13 * r, normal + 3 * r, est + MPC_EST_STRIDE * r);
 }
+
+// Direct access to the two dense factorisation lane programs for tests/test_warp_emu.py:
+// A (n x n SPD, row-major, n a multiple of 6, n <= pcap in {60, 120}) -> W = chol(A)^-1 (lower, row-major).
+template <int PCAP>
+static void chol_inv_t(const double* A, int n, double* W) {
+  std::vector<double> Wp((size_t)PCAP * (PCAP + 1) / 2 + 8, 0.0), colb(2 * PCAP, 0.0), dinv(PCAP, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < i; ++k) Wp[mpc::tri(i) + k] = A[(size_t)i * n + k];
+    colb[i] = A[(size_t)i * n + i];
+  }
+  mpc::cholesky_blocked<PCAP>(Wp.data(), colb.data(), dinv.data(), n);
+  mpc::invert_lower_blocked<PCAP>(Wp.data(), dinv.data(), n);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < n; ++k) W[(size_t)i * n + k] = k < i ? Wp[mpc::tri(i) + k] : (k == i ? dinv[i] : 0.0);
+}
+
+extern "C" int mpc_emu_chol_inv(const double* A, int n, int pcap, double* W) {
+  if (n <= 0 || n % 6 || n > pcap) return -1;
+  if (pcap == 60) chol_inv_t<60>(A, n, W);
+  else if (pcap == 120) chol_inv_t<120>(A, n, W);
+  else return -1;
+  return 0;
+}
