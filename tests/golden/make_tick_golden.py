@@ -115,3 +115,4 @@ if __name__ == "__main__":
     run_case("aliengo_trot", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True)
     run_case("aliengo_walk_flat", RobotType.ALIENGO, GaitType.WALK, True, 60, 2, False)
     run_case("a1_bound", RobotType.A1, GaitType.BOUND, False, 60, 3, True)
+    run_case("go1_trot_flat", RobotType.GO1, GaitType.TROT, True, 60, 4, False)

@@ -34,7 +34,7 @@ def _gpu_tick_fn():
 
 
 @pytest.mark.parametrize("device_estimator", [False, True])
-@pytest.mark.parametrize("name", ["aliengo_trot", "aliengo_walk_flat", "a1_bound"])
+@pytest.mark.parametrize("name", ["aliengo_trot", "aliengo_walk_flat", "a1_bound", "go1_trot_flat"])
 def test_gpu_tick_replay_matches_reference_python(name, device_estimator):
     from test_tick import replay
     w = replay(name, _gpu_tick_fn(), device_estimator)

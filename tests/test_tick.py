@@ -50,7 +50,7 @@ def _emu_tick(state, dof, est, cmd, with_w, gait, rtype, flat, warm=None):
 
 
 @pytest.mark.parametrize("device_estimator", [False, True])
-@pytest.mark.parametrize("name", ["aliengo_trot", "aliengo_walk_flat", "a1_bound"])
+@pytest.mark.parametrize("name", ["aliengo_trot", "aliengo_walk_flat", "a1_bound", "go1_trot_flat"])
 def test_tick_replay_matches_reference_python(name, device_estimator):
     w = replay(name, _emu_tick, device_estimator)
     print(name, w)
