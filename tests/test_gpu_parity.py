@@ -153,6 +153,27 @@ def test_standing_contact_table_uses_overflow_kernel(oracle_mod, horizon):
     assert out["info"][:, 7].max() > 6 * horizon      # the overflow path was really exercised
 
 
+@pytest.mark.parametrize("name,table", [
+    ("three_leg_stance", np.tile([1, 1, 1, 0], 10).astype(np.float32)),
+    ("all_swing", np.zeros(40, np.float32)),
+    ("flight_step", np.concatenate([np.zeros(4), np.tile([1, 0, 0, 1], 9)]).astype(np.float32)),
+    ("single_leg", np.tile([1, 0, 0, 0], 10).astype(np.float32)),
+])
+def test_contact_tables_outside_the_reference_gaits(oracle_mod, name, table):
+    """GPU twin of tests/test_warp_emu.py::test_contact_tables_outside_the_reference_gaits: 3-leg
+    stance (overflow instantiation), pure flight (no free polish coordinate), a flight step, one
+    stance leg."""
+    from rl_mpc_locomotion_b200 import synth
+    from rl_mpc_locomotion_b200.records import REC_CONTACT
+    rec, rt, params, _ = synth.make_batch(24, 10, seed=9)
+    rec = rec.copy()
+    rec[:, REC_CONTACT:REC_CONTACT + 40] = table
+    out = _gpu_solve(rec, rt, params, 10)
+    f0, ff, st = oracle_mod.solve_records(rec, 10, params, rt, mode=oracle_mod.COLD, full=True)
+    assert np.array_equal(out["status"], st)
+    assert np.abs(out["grf_full"] - ff).max() < TOL_N
+
+
 def test_launch_order_hint_does_not_change_results():
     import torch
     from rl_mpc_locomotion_b200 import synth
