@@ -239,7 +239,9 @@ typedef struct MpcB200TickParams {
  *   d_torques [n, 12] float32 out
  *   d_grf0   [n, 12] float32 out or NULL: written for robots whose MPC fired this tick
  *   d_records[n, MPC_REC_STRIDE(h)] float32 out or NULL: the QP record built this tick (tests)
- *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise
+ *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise; a robot whose
+ *            solve did not end in MPC_STATUS_SOLVED keeps the feed-forward forces of its previous
+ *            MPC tick (hold-last fallback; d_grf0 still shows what the failed solve produced)
  *   d_warm   [n, MPC_WARM_STRIDE(h)] float64 in/out or NULL: see mpc_b200_solve_batch
  *   d_order  [n] int32 or NULL: launch order (CTA b runs robot d_order[b]), a pure scheduling
  *            hint as in mpc_b200_solve_batch; consecutive MPC solves of a robot need similar

@@ -198,7 +198,10 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     if (lane == 0) reinterpret_cast<int*>(st_s)[MPC_ST_ITERS] = (int)info_s[mpc::INFO_ITERS];
     if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
   }
-  mpc::tick_post(est_s, geom_s, do_solve ? grf_s : nullptr, st_s, legs_s, torques + (size_t)robot * 12, lane);
+  // fallback policy: forces of a solve that did not reach OSQP_SOLVED are not applied, the previous
+  // MPC tick's f_ff stays in force (the reference would raise on its empty result, mpc_osqp.cc:786-794)
+  const bool apply = do_solve && stat_s[0] == MPC_STATUS_SOLVED;
+  mpc::tick_post(est_s, geom_s, apply ? grf_s : nullptr, st_s, legs_s, torques + (size_t)robot * 12, lane);
   for (int i = lane; i < MPC_TICK_STATE_STRIDE; i += MPC_NL) state[(size_t)robot * MPC_TICK_STATE_STRIDE + i] = st_s[i];
   if (solved && lane == 0) solved[robot] = stat_s[0];
 }

@@ -95,8 +95,9 @@ class BatchedLocomotion:
                                           p(self.torques), p(self.grf0), p(records_out), p(self.solved),
                                           p(self.warm), p(self.order), C.c_void_p(stream))
         _lib.check(rc, "mpc_b200_tick")
-        if self.longest_first and self._ticks % self.tick_params.iters_between_mpc == 0:
-            # this was (for robots never reset individually) an MPC tick: sort for the next one
+        if self.longest_first and (self._ticks + 1) % self.tick_params.iters_between_mpc == 0:
+            # this was (for robots never reset individually) an MPC tick - the kernel solves when the
+            # incremented iterationCounter is a multiple of iters_between_mpc: sort for the next one
             iters = self.state.view(torch.int32)[:, 91]          # MPC_ST_ITERS
             self.order = torch.argsort(iters, descending=True, stable=True).to(torch.int32)
         self._ticks += 1

@@ -105,3 +105,26 @@ def test_locomotion_safe_flag_replicates_reference_quirks():
         cmd = np.zeros((1, 16), np.float32)
         emu.tick(state, dof, None, cmd, 0, [0], params_table(), geom_table(), [0], body=body)
         assert int(state.view(np.int32)[0, 90]) == expect, (roll, pitch, expect)
+
+
+def test_failed_solve_holds_last_forces():
+    """Fallback policy of the tick: a solve that does not reach OSQP_SOLVED is reported in `solved`
+    and NOT applied - the previous MPC tick's feed-forward forces stay in the state row."""
+    g = np.load(os.path.join(GOLD, "tick_golden_aliengo_trot.npz"))
+    state = initial_tick_state([0])
+    def est_row(t):
+        return np.concatenate([g["vBody"][t], g["omegaBody"][t], g["rpyBody"][t], g["groundR"][t]]).astype(np.float32)[None]
+    args = lambda t: (g["dof"][t][None], est_row(t), g["cmd"][t][None], 1, [0], params_table(), geom_table(), [0])
+    emu.tick(state, *args(0))                             # iterationCounter 1: no MPC
+    out1 = emu.tick(state, *args(1))                      # MPC tick, solved
+    assert out1["solved"][0] == 1
+    fff1 = state[0, 58:70].copy()
+    assert np.abs(fff1).max() > 1.0
+    emu.tick(state, *args(2))                             # non-MPC tick
+    out3 = emu.tick(state, *args(3), params=emu.default_params(max_iter=25))   # MPC tick, cut off at 25 iterations
+    assert out3["solved"][0] == -2                        # OSQP_MAX_ITER_REACHED
+    assert np.abs(out3["grf0"]).max() > 0                 # the failed solve's iterate is still reported
+    assert np.array_equal(state[0, 58:70], fff1)          # ... but not applied
+    emu.tick(state, *args(4))
+    out5 = emu.tick(state, *args(5))
+    assert out5["solved"][0] == 1 and not np.array_equal(state[0, 58:70], fff1)

@@ -85,7 +85,7 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
       reinterpret_cast<int*>(st)[MPC_ST_ITERS] = (int)info[mpc::INFO_ITERS];
       if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
     }
-    mpc::tick_post(e, g, do_solve ? grf : nullptr, st, legs, torques + (size_t)r * 12);
+    mpc::tick_post(e, g, (do_solve && st_code == MPC_STATUS_SOLVED) ? grf : nullptr, st, legs, torques + (size_t)r * 12);
     if (solved) solved[r] = st_code;
   }
   return 0;
