@@ -67,9 +67,12 @@ extern "C" {
 #define MPC_STATUS_MAX_ITER       -2   /* mirrors OSQP_MAX_ITER_REACHED       */
 #define MPC_STATUS_NON_FINITE     -7   /* residuals diverged / NaN (mirrors OSQP_NON_CVX): forces zeroed,
                                           warm state untouched; the reference returns an empty vector   */
-#define MPC_STATUS_POLISH_OVERFLOW -90 /* internal: more free coordinates than the fast kernel's polish
-                                          buffer (> 2h stance leg-steps); re-solved by the overflow kernel
-                                          inside the same mpc_b200_solve_batch call, never returned    */
+#define MPC_STATUS_POLISH_OVERFLOW -90 /* more free coordinates than the fast kernel's polish buffer (> 2h stance
+                                          leg-steps).  mpc_b200_solve_batch re-solves such robots with the
+                                          overflow kernel inside the same call and never returns this code;
+                                          mpc_b200_tick (no overflow pass) reports it in d_solved and applies
+                                          the UN-polished ADMM solution (see mpc_b200_tick)              */
+#define MPC_STATUS_BAD_INDEX      -91  /* d_robot_type[robot] outside [0, n_types): forces zeroed, robot skipped */
 
 /* Solver modes */
 #define MPC_MODE_OSQP   0  /* reproduce the reference's OSQP run step for step (fp64): Ruiz
@@ -119,7 +122,10 @@ int  mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta,
  * Batched solve: n_robots independent QPs, one warp per robot.
  *   d_records      [n_robots, MPC_REC_STRIDE(h)] float32, device
  *   d_robot_params [n_types, MPC_ROBOT_PARAMS_STRIDE] float32, device
- *   d_robot_type   [n_robots] int32 device, or NULL (all robots type 0)
+ *   d_robot_type   [n_robots] int32 device, or NULL (all robots type 0); an entry outside
+ *                  [0, n_types) gives that robot MPC_STATUS_BAD_INDEX and zero forces (checked on
+ *                  the device; the host-pointer entry point returns MPC_B200_EINVAL instead)
+ *   n_types        rows of d_robot_params (>= 1)
  *   d_grf0         [n_robots, 12] float32 device: horizon-0 contact forces,
  *                  NEGATED QP solution exactly as mpc_osqp.cc:789-790 returns
  *   d_grf_full     [n_robots, 12*h] float32 device or NULL (full horizon)
@@ -131,7 +137,8 @@ int  mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta,
  *                  workspace state (settings.warm_start = true, mpc_osqp.cc:708, :760-778).
  *                  Rows with flag 0 start cold (= osqp_setup on the first call); every solve
  *                  leaves its iterates / rho / q for the next one.  NULL = cold start always.
- *   d_order        [n_robots] int32 device or NULL: launch order (CTA b solves robot d_order[b]).
+ *   d_order        [n_robots] int32 device or NULL: launch order (CTA b solves robot d_order[b]); must be
+ *                  a permutation of 0..n_robots-1 (entries outside that range are skipped on the device).
  *                  Purely a scheduling hint - results are identical: OSQP's iteration count varies
  *                  50..350 per robot and the launch ends with its slowest robot, so a control loop
  *                  can pass last tick's robots sorted by descending iteration count
@@ -143,6 +150,7 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings,
                          const float* d_records,
                          const float* d_robot_params,
                          const int32_t* d_robot_type,
+                         int n_types,
                          int n_robots,
                          float* d_grf0,
                          float* d_grf_full,
@@ -163,6 +171,7 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
                               const float* h_records,
                               const float* h_robot_params,
                               const int32_t* h_robot_type,
+                              int n_types,
                               int n_robots,
                               float* h_grf0,
                               float* h_grf_full,
@@ -195,8 +204,15 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings,
 #define MPC_EST_RPYBODY    6
 #define MPC_EST_GROUNDR    9
 #define MPC_EST_STRIDE    18
-/* commands per robot (float32): vx, vy, yaw rate, then 13 MPC weights (used when has_weights) */
+/* commands per robot (float32): vx, vy, yaw rate [, 13 MPC weights]; the row stride is
+ * MpcB200TickParams.cmd_stride = 3 (Isaac `commands[N,3]`, aliengo.py:233) or MPC_CMD_STRIDE */
 #define MPC_CMD_STRIDE    16
+/* per-robot FSM gate of the tick (d_active), see mpc_b200_tick */
+#define MPC_TICK_SKIP        0   /* robot not in Locomotion: nothing read, nothing written                  */
+#define MPC_TICK_RUN         1   /* run the tick (FSM_OperatingMode.TEST, ControlFSM.py:80-81)               */
+#define MPC_TICK_CHECK_RUN   2   /* NORMAL mode: locomotionSafe() first; unsafe -> zero torques, state untouched
+                                    except MPC_ST_UNSAFE (ControlFSM.py:84-95: the tick is not run)         */
+#define MPC_TICK_CHECK_ONLY  3   /* evaluate locomotionSafe() only (a transition was requested): zero torques  */
 /* persistent per-robot tick state (float32 row; the first six slots hold int32 bit patterns) */
 #define MPC_ST_COUNTER     0   /* int  iterationCounter                         */
 #define MPC_ST_FIRSTRUN    1   /* int                                           */
@@ -222,7 +238,10 @@ typedef struct MpcB200TickParams {
   int   iters_between_mpc; /* int(27/(1000*dt)) = 2 (RobotRunnerMin.py:21-22)        */
   int   flat_ground;       /* Parameters.flat_ground                                */
   float bonus_swing;       /* Parameters.cmpc_bonus_swing                           */
-  int   reserved[4];
+  int   cmd_stride;        /* floats per row of d_cmd: 3 or MPC_CMD_STRIDE (0 = MPC_CMD_STRIDE) */
+  int   reserved[3];
+  float act_scale[12];     /* Parameters.MPC_param_scale (Parameters.py:25-28)      */
+  float act_const[12];     /* Parameters.MPC_param_const (Parameters.py:30-33)      */
 } MpcB200TickParams;
 
 /*
@@ -232,16 +251,29 @@ typedef struct MpcB200TickParams {
  *            or NULL; when given, StateEstimator.update runs on the device
  *   d_est    [n, MPC_EST_STRIDE] float32 or NULL: precomputed StateEstimator.update outputs
  *            (exactly one of d_body / d_est must be non-NULL)
- *   d_cmd    [n, MPC_CMD_STRIDE] float32; has_weights != 0 -> weights from d_cmd, else robot default
+ *   d_cmd    [n, tick->cmd_stride] float32: vx, vy, yaw rate (+ 13 weights when the stride is 16)
+ *   has_weights != 0 (needs cmd_stride 16, no d_actions): MPC weights from d_cmd[:, 3:16]
+ *   d_actions [n, 12] float32 policy actions in [-1, 1] or NULL.  When given, the MPC weights are
+ *            actions * tick->act_scale + tick->act_const (float32 multiply then add, 13th weight 0) -
+ *            the rescale of pre_physics_step (aliengo.py:237-245, 253) done on the device.
+ *            Neither d_actions nor has_weights: the robot's default weights (Quadruped.py:30-34).
  *   d_gait   [n] int32 gait ids (ConvexMPCLocomotion.py:227-241) or NULL (trot)
  *   d_robot_params [n_types, 12], d_robot_geom [n_types, MPC_GEOM_STRIDE], d_robot_type [n] or NULL
+ *            (entries outside [0, n_types): robot skipped, d_solved = MPC_STATUS_BAD_INDEX, zero torques)
+ *   d_active [n] int32 MPC_TICK_* or NULL (all MPC_TICK_RUN): the FSM shell's per-robot gate
+ *            (RobotRunnerFSM.py:55-69 -> ControlFSM.runFSM, ControlFSM.py:78-104).  The safety check
+ *            needs d_body (the world roll / pitch come from StateEstimator.update).
  *   d_state  [n, MPC_TICK_STATE_STRIDE] float32, read and written
  *   d_torques [n, 12] float32 out
  *   d_grf0   [n, 12] float32 out or NULL: written for robots whose MPC fired this tick
  *   d_records[n, MPC_REC_STRIDE(h)] float32 out or NULL: the QP record built this tick (tests)
  *   d_solved [n] int32 out or NULL: OSQP status when the MPC fired, 0 otherwise; a robot whose
  *            solve did not end in MPC_STATUS_SOLVED keeps the feed-forward forces of its previous
- *            MPC tick (hold-last fallback; d_grf0 still shows what the failed solve produced)
+ *            MPC tick (hold-last fallback; d_grf0 still shows what the failed solve produced).
+ *            MPC_STATUS_POLISH_OVERFLOW (contact tables with > 2h stance leg-steps, which none of
+ *            the reference's gaits produces - tests/test_host.py checks every gait) can appear here:
+ *            the tick has no overflow pass, it applies the converged but UN-polished ADMM solution
+ *            and leaves d_warm untouched for that robot.
  *   d_warm   [n, MPC_WARM_STRIDE(h)] float64 in/out or NULL: see mpc_b200_solve_batch
  *   d_order  [n] int32 or NULL: launch order (CTA b runs robot d_order[b]), a pure scheduling
  *            hint as in mpc_b200_solve_batch; consecutive MPC solves of a robot need similar
@@ -250,9 +282,10 @@ typedef struct MpcB200TickParams {
  */
 int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick,
                   const float* d_dof, const float* d_body, const float* d_est, const float* d_cmd,
-                  int has_weights,
+                  int has_weights, const float* d_actions,
                   const int32_t* d_gait, const float* d_robot_params, const float* d_robot_geom,
-                  const int32_t* d_robot_type, int n_robots, float* d_state, float* d_torques,
+                  const int32_t* d_robot_type, int n_types, int n_robots, const int32_t* d_active,
+                  float* d_state, float* d_torques,
                   float* d_grf0, float* d_records, int32_t* d_solved, double* d_warm,
                   const int32_t* d_order, void* stream);
 

@@ -13,7 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPC_B200_LIB", os.path.join(_HERE, "libmpc_b200.so"))  # env override: A/B builds
 
 MODE_OSQP, MODE_FIXED = 0, 1
-STATUS_SOLVED, STATUS_MAX_ITER = 1, -2
+STATUS_SOLVED, STATUS_MAX_ITER, STATUS_NON_FINITE, STATUS_POLISH_OVERFLOW, STATUS_BAD_INDEX = 1, -2, -7, -90, -91
+TICK_SKIP, TICK_RUN, TICK_CHECK_RUN, TICK_CHECK_ONLY = 0, 1, 2, 3     # MPC_TICK_* (d_active gate)
+# reference Parameters.MPC_param_scale / MPC_param_const (Parameters.py:25-33)
+ACT_SCALE = (4.0, 4.0, 4.0, 20.0, 20.0, 20.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
+ACT_CONST = (5.0, 5.0, 5.0, 50.0, 50.0, 50.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
 EXPORTS = ("mpc_b200_default_settings", "mpc_b200_version", "mpc_b200_last_error",
            "mpc_b200_device_count", "mpc_b200_kernel_info", "mpc_b200_solve_batch",
            "mpc_b200_solve_batch_host", "mpc_b200_debug_build_qp", "mpc_b200_tick")
@@ -36,7 +40,16 @@ class Settings(C.Structure):
 class TickParams(C.Structure):
     """Mirror of ``MpcB200TickParams``."""
     _fields_ = [("dt", C.c_float), ("iters_between_mpc", C.c_int), ("flat_ground", C.c_int),
-                ("bonus_swing", C.c_float), ("reserved", C.c_int * 4)]
+                ("bonus_swing", C.c_float), ("cmd_stride", C.c_int), ("reserved", C.c_int * 3),
+                ("act_scale", C.c_float * 12), ("act_const", C.c_float * 12)]
+
+
+def tick_params(dt=0.01, iters_between_mpc=2, flat_ground=False, bonus_swing=0.0, cmd_stride=16,
+                act_scale=ACT_SCALE, act_const=ACT_CONST) -> TickParams:
+    tp = TickParams(dt, iters_between_mpc, int(flat_ground), bonus_swing, cmd_stride)
+    tp.act_scale[:] = act_scale
+    tp.act_const[:] = act_const
+    return tp
 
 
 _lib = None
@@ -59,14 +72,15 @@ def lib():
         L.mpc_b200_device_count.restype = C.c_int
         L.mpc_b200_kernel_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.mpc_b200_kernel_info.restype = C.c_int
-        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_solve_batch.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                           vp, vp]
         L.mpc_b200_solve_batch.restype = C.c_int
-        L.mpc_b200_solve_batch_host.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, vp, vp, vp]
+        L.mpc_b200_solve_batch_host.argtypes = [C.POINTER(Settings), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
         L.mpc_b200_solve_batch_host.restype = C.c_int
         L.mpc_b200_debug_build_qp.argtypes = [C.POINTER(Settings), vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_debug_build_qp.restype = C.c_int
-        L.mpc_b200_tick.argtypes = [C.POINTER(Settings), C.POINTER(TickParams), vp, vp, vp, vp, C.c_int, vp, vp, vp,
-                                    vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_tick.argtypes = [C.POINTER(Settings), C.POINTER(TickParams), vp, vp, vp, vp, C.c_int, vp, vp, vp, vp,
+                                    vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tick.restype = C.c_int
         _lib = L
     return _lib

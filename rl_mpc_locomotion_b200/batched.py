@@ -72,7 +72,8 @@ class BatchedConvexMpc:
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = _lib.lib().mpc_b200_solve_batch(C.byref(self.settings), ptr(records), ptr(self.robot_params),
-                                                 ptr(robot_type), n, ptr(grf0), ptr(gfull), ptr(st),
+                                                 ptr(robot_type), int(self.robot_params.shape[0]), n, ptr(grf0),
+                                                 ptr(gfull), ptr(st),
                                                  ptr(resid), ptr(inf), ptr(warm), ptr(order), C.c_void_p(stream))
         _lib.check(rc, "mpc_b200_solve_batch")
         if full:
@@ -99,14 +100,14 @@ def solve_host(records: np.ndarray, horizon: int = 10, robot_params=None, robot_
     rec = np.ascontiguousarray(records, dtype=np.float32)
     n = rec.shape[0]
     assert rec.shape[1] == rec_stride(horizon)
-    rp = np.ascontiguousarray(params_table() if robot_params is None else robot_params, dtype=np.float32)
+    rp = np.ascontiguousarray(params_table() if robot_params is None else robot_params, dtype=np.float32).reshape(-1, 12)
     rt = None if robot_type is None else np.ascontiguousarray(robot_type, dtype=np.int32)
     grf0 = np.empty((n, 12), np.float32)
     gfull = np.empty((n, 12 * horizon), np.float32) if full else None
     status = np.empty((n,), np.int32)
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
-    rc = _lib.lib().mpc_b200_solve_batch_host(C.byref(s), vp(rec), vp(rp), vp(rt), n, vp(grf0), vp(gfull),
-                                              vp(status))
+    rc = _lib.lib().mpc_b200_solve_batch_host(C.byref(s), vp(rec), vp(rp), vp(rt), int(rp.shape[0]), n, vp(grf0),
+                                              vp(gfull), vp(status))
     _lib.check(rc, "mpc_b200_solve_batch_host")
     out = {"grf0": grf0, "status": status}
     if full:
@@ -142,8 +143,8 @@ def solve_host_pinned(records, robot_type, robot_params, horizon, steps, warmup=
     vp = lambda t: C.c_void_p(t.data_ptr())
 
     def one():
-        rc = _lib.lib().mpc_b200_solve_batch_host(C.byref(s), vp(t_rec), vp(t_rp), vp(t_rt), n, vp(t_grf), None,
-                                                  vp(t_st))
+        rc = _lib.lib().mpc_b200_solve_batch_host(C.byref(s), vp(t_rec), vp(t_rp), vp(t_rt), int(t_rp.shape[0]), n,
+                                                  vp(t_grf), None, vp(t_st))
         _lib.check(rc, "mpc_b200_solve_batch_host")
 
     for _ in range(warmup):

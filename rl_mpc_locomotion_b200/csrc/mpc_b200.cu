@@ -85,7 +85,7 @@ struct KernelCfg {
 template <int H, bool WARM, int PCAP, bool ONLY_OVERFLOW>
 __global__ void __launch_bounds__(MPC_NL, (PCAP > 6 * H ? 1 : MPC_MIN_CTAS))
 mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
-                 const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type,
+                 const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type, int n_types,
                  int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
                  int32_t* __restrict__ status, float* __restrict__ resid, double* __restrict__ info,
                  double* __restrict__ dbg, double* __restrict__ warm, const int32_t* __restrict__ order) {
@@ -98,8 +98,17 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
   const int lane = threadIdx.x;
   if ((int)blockIdx.x >= n_robots) return;
   const int robot = order ? order[blockIdx.x] : (int)blockIdx.x;   // scheduling hint only
+  if (robot < 0 || robot >= n_robots) return;                      // not a permutation entry: skipped
   if constexpr (ONLY_OVERFLOW) {
     if (status[robot] != MPC_STATUS_POLISH_OVERFLOW) return;   // uniform per CTA
+  }
+  const int type = robot_type ? robot_type[robot] : 0;
+  if (type < 0 || type >= n_types) {   // bad robot type: report, never index robot_params with it
+    if (lane < 12) grf0[(size_t)robot * 12 + lane] = 0.0f;
+    if (grf_full)
+      for (int i = lane; i < 12 * H; i += MPC_NL) grf_full[(size_t)robot * 12 * H + i] = 0.0f;
+    if (status && lane == 0) status[robot] = MPC_STATUS_BAD_INDEX;
+    return;
   }
 
   // stage the robot's state block with one TMA bulk copy while the tables are built
@@ -108,7 +117,6 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_load_1d(rec_s, records + (size_t)robot * K::REC_FLOATS, K::REC_BYTES, bar);
   }
-  const int type = robot_type ? robot_type[robot] : 0;
   if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
   mpc::fill_tables<H, PCAP>(sm, prm.dt, lane);
   WSYNC();
@@ -140,9 +148,10 @@ template <int H, bool WARM>
 __global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
 mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const float* __restrict__ dof,
                 const float* __restrict__ body, const float* __restrict__ est, const float* __restrict__ cmd,
-                int has_weights,
+                int has_weights, const float* __restrict__ actions,
                 const int32_t* __restrict__ gait, const float* __restrict__ robot_params,
-                const float* __restrict__ robot_geom, const int32_t* __restrict__ robot_type, int n_robots,
+                const float* __restrict__ robot_geom, const int32_t* __restrict__ robot_type, int n_types, int n_robots,
+                const int32_t* __restrict__ active,
                 float* __restrict__ state, float* __restrict__ torques, float* __restrict__ grf0,
                 float* __restrict__ records, int32_t* __restrict__ solved, double* __restrict__ warm,
                 const int32_t* __restrict__ order) {
@@ -163,14 +172,33 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
   const int lane = threadIdx.x;
   if ((int)blockIdx.x >= n_robots) return;
   const int robot = order ? order[blockIdx.x] : (int)blockIdx.x;   // scheduling hint only
+  if (robot < 0 || robot >= n_robots) return;
+  const int gate = active ? active[robot] : MPC_TICK_RUN;          // the FSM shell's per-robot gate
+  if (gate == MPC_TICK_SKIP) return;
   const int type = robot_type ? robot_type[robot] : 0;
+  if (type < 0 || type >= n_types) {
+    if (lane < 12) torques[(size_t)robot * 12 + lane] = 0.0f;
+    if (solved && lane == 0) solved[robot] = MPC_STATUS_BAD_INDEX;
+    return;
+  }
   for (int i = lane; i < MPC_TICK_STATE_STRIDE; i += MPC_NL) st_s[i] = state[(size_t)robot * MPC_TICK_STATE_STRIDE + i];
   if (lane < 24) {
     dof_s[lane] = dof[(size_t)robot * 24 + lane];
     geom_s[lane] = robot_geom[(size_t)type * MPC_GEOM_STRIDE + lane];
   }
   if (est && lane < 18) est_s[lane] = est[(size_t)robot * MPC_EST_STRIDE + lane];
-  if (lane < 16) cmd_s[lane] = cmd[(size_t)robot * MPC_CMD_STRIDE + lane];
+  // commands: vx, vy, yaw rate [+ 13 weights]; with `actions` the weights are actions * scale + const
+  // (two float32 roundings as torch.mul(...).add(...), aliengo.py:237-245; 13th weight 0, :253)
+  const int cstride = tp.cmd_stride > 0 ? tp.cmd_stride : MPC_CMD_STRIDE;
+  if (lane < 16) {
+    float v = 0.0f;
+    if (lane < 3) v = cmd[(size_t)robot * cstride + lane];
+    else if (actions) v = lane < 15 ? __fadd_rn(__fmul_rn(actions[(size_t)robot * 12 + lane - 3], tp.act_scale[lane - 3]),
+                                                 tp.act_const[lane - 3]) : 0.0f;
+    else if (has_weights && cstride >= MPC_CMD_STRIDE) v = cmd[(size_t)robot * cstride + lane];
+    cmd_s[lane] = v;
+  }
+  const bool with_weights = actions != nullptr || (has_weights && cstride >= MPC_CMD_STRIDE);
   if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
   if (lane == 0) stat_s[0] = 0;
   for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) rec_s[i] = 0.0f;
@@ -182,11 +210,23 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
   const bool have_rp = !est;   // grf_s[0..1] temporarily holds the world roll / pitch (float16 values)
   const float roll16 = have_rp ? grf_s[0] : 0.0f, pitch16 = have_rp ? grf_s[1] : 0.0f;
   const int g = gait ? gait[robot] : 0;
-  const int do_solve = mpc::tick_pre<H>(dof_s, est_s, cmd_s, has_weights, g, geom_s, tp, st_s, rec_s, legs_s, lane);
-  if (have_rp && lane == 0) {
+  mpc::tick_legs(dof_s, geom_s, st_s, rec_s, legs_s, lane);
+  // FSM_State_Locomotion.checkTransition -> locomotionSafe() comes BEFORE the control step
+  // (ControlFSM.py:84-95): an unsafe robot is not ticked, its commands stay zero
+  int unsafe = 0;
+  if (have_rp) {
     const float rp2[2] = {roll16, pitch16};
-    reinterpret_cast<int*>(st_s)[MPC_ST_UNSAFE] = mpc::locomotion_unsafe(rp2, legs_s + mpc::LG_P, mpc::LG_STRIDE);
+    unsafe = mpc::locomotion_unsafe(rp2, legs_s + mpc::LG_P, mpc::LG_STRIDE);   // uniform (shared-memory inputs)
   }
+  if (gate == MPC_TICK_CHECK_ONLY || (gate == MPC_TICK_CHECK_RUN && unsafe)) {
+    if (lane < 12) torques[(size_t)robot * 12 + lane] = 0.0f;
+    if (lane == 0) reinterpret_cast<int*>(state)[(size_t)robot * MPC_TICK_STATE_STRIDE + MPC_ST_UNSAFE] = unsafe;
+    if (solved && lane == 0) solved[robot] = 0;
+    return;
+  }
+  const int do_solve = mpc::tick_pre<H>(est_s, cmd_s, with_weights ? cmd_s + 3 : nullptr, g, geom_s, tp, st_s, rec_s,
+                                        legs_s, lane);
+  if (have_rp && lane == 0) reinterpret_cast<int*>(st_s)[MPC_ST_UNSAFE] = unsafe;
   if (records)
     for (int i = lane; i < K::REC_FLOATS; i += MPC_NL) records[(size_t)robot * K::REC_FLOATS + i] = rec_s[i];
   if (do_solve) {
@@ -199,8 +239,10 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
   }
   // fallback policy: forces of a solve that did not reach OSQP_SOLVED are not applied, the previous
-  // MPC tick's f_ff stays in force (the reference would raise on its empty result, mpc_osqp.cc:786-794)
-  const bool apply = do_solve && stat_s[0] == MPC_STATUS_SOLVED;
+  // MPC tick's f_ff stays in force (the reference would raise on its empty result, mpc_osqp.cc:786-794).
+  // MPC_STATUS_POLISH_OVERFLOW = OSQP_SOLVED whose polish did not fit this kernel's buffer (no reference
+  // gait gets there): the converged, un-polished ADMM solution is applied.
+  const bool apply = do_solve && (stat_s[0] == MPC_STATUS_SOLVED || stat_s[0] == MPC_STATUS_POLISH_OVERFLOW);
   mpc::tick_post(est_s, geom_s, apply ? grf_s : nullptr, st_s, legs_s, torques + (size_t)robot * 12, lane);
   for (int i = lane; i < MPC_TICK_STATE_STRIDE; i += MPC_NL) state[(size_t)robot * MPC_TICK_STATE_STRIDE + i] = st_s[i];
   if (solved && lane == 0) solved[robot] = stat_s[0];
@@ -208,8 +250,9 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
 
 template <int H>
 int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* body,
-                const float* est, const float* cmd, int has_weights, const int32_t* gait, const float* rp, const float* geom,
-                const int32_t* rt, int n, float* state, float* torques, float* grf0, float* records,
+                const float* est, const float* cmd, int has_weights, const float* actions, const int32_t* gait,
+                const float* rp, const float* geom, const int32_t* rt, int n_types, int n, const int32_t* active,
+                float* state, float* torques, float* grf0, float* records,
                 int32_t* solved, double* warm, const int32_t* order, cudaStream_t stream) {
   using T = TickCfg<H>;
   static std::once_flag once;
@@ -222,13 +265,13 @@ int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const fl
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem, tick)");
   if (n <= 0) return MPC_B200_OK;
   if (warm)
-    mpc_tick_kernel<H, true><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp,
-                                                                  geom, rt, n, state, torques, grf0, records, solved, warm,
-                                                                  order);
+    mpc_tick_kernel<H, true><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, actions,
+                                                                  gait, rp, geom, rt, n_types, n, active, state, torques,
+                                                                  grf0, records, solved, warm, order);
   else
-    mpc_tick_kernel<H, false><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, gait, rp,
-                                                                   geom, rt, n, state, torques, grf0, records, solved, nullptr,
-                                                                   order);
+    mpc_tick_kernel<H, false><<<n, MPC_NL, T::SMEM_BYTES, stream>>>(prm, tp, dof, body, est, cmd, has_weights, actions,
+                                                                   gait, rp, geom, rt, n_types, n, active, state, torques,
+                                                                   grf0, records, solved, nullptr, order);
   CK(cudaGetLastError());
   return MPC_B200_OK;
 }
@@ -280,7 +323,7 @@ int check_settings(const MpcB200Settings* s) {
 }
 
 template <int H, bool WARM>
-int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n, float* grf0,
+int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int nt, int n, float* grf0,
              float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
              const int32_t* order, cudaStream_t stream) {
   using K = KernelCfg<H>;
@@ -299,12 +342,12 @@ int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, con
   // the overflow pass needs the per-robot status even when the caller does not want it
   int32_t* st = status;
   if (!st) CK(cudaMallocAsync((void**)&st, (size_t)n * sizeof(int32_t), stream));
-  mpc_solve_kernel<H, WARM, 6 * H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, st,
+  mpc_solve_kernel<H, WARM, 6 * H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
                                                                                resid, info, dbg, warm, order);
   CK(cudaGetLastError());
   // robots whose polish did not fit the fast kernel's buffer (> 2H stance leg-steps): every other
   // CTA of this launch exits at once
-  mpc_solve_kernel<H, WARM, 12 * H, true><<<n, MPC_NL, KB::SMEM_BYTES, stream>>>(prm, rec, rp, rt, n, grf0, grf_full, st,
+  mpc_solve_kernel<H, WARM, 12 * H, true><<<n, MPC_NL, KB::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
                                                                                resid, info, dbg, warm, order);
   CK(cudaGetLastError());
   if (!status) CK(cudaFreeAsync(st, stream));
@@ -312,21 +355,21 @@ int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, con
 }
 
 template <int H>
-int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int n,
+int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int nt, int n,
            float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
            const int32_t* order, cudaStream_t stream) {
   if (warm)
-    return launch_w<H, true>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
-  return launch_w<H, false>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, nullptr, order, stream);
+    return launch_w<H, true>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
+  return launch_w<H, false>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, nullptr, order, stream);
 }
 
-int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int n,
+int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int nt, int n,
              float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
              const int32_t* order, cudaStream_t stream) {
   const mpc::SolveParams prm = to_params(*s);
   if (s->horizon == 10)
-    return launch<10>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
-  return launch<16>(prm, rec, rp, rt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
+    return launch<10>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
+  return launch<16>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
 }
 
 // grow-only device scratch for the host-pointer convenience entry points
@@ -404,13 +447,13 @@ int mpc_b200_kernel_info(int horizon, int* smem_bytes, int* robots_per_cta, int*
 }
 
 int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records,
-                         const float* d_robot_params, const int32_t* d_robot_type, int n_robots,
+                         const float* d_robot_params, const int32_t* d_robot_type, int n_types, int n_robots,
                          float* d_grf0, float* d_grf_full, int32_t* d_status, float* d_resid,
                          double* d_info, double* d_warm, const int32_t* d_order, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
-  if (n_robots < 0 || (n_robots > 0 && (!d_records || !d_robot_params || !d_grf0))) {
-    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+  if (n_robots < 0 || n_types < 1 || (n_robots > 0 && (!d_records || !d_robot_params || !d_grf0))) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch / n_types < 1");
     return MPC_B200_EINVAL;
   }
   if (mpc_b200_device_count() <= 0) {
@@ -418,28 +461,31 @@ int mpc_b200_solve_batch(const MpcB200Settings* settings, const float* d_records
     return MPC_B200_ENOGPU;
   }
   if (n_robots == 0) return MPC_B200_OK;
-  return dispatch(settings, d_records, d_robot_params, d_robot_type, n_robots, d_grf0, d_grf_full, d_status,
+  return dispatch(settings, d_records, d_robot_params, d_robot_type, n_types, n_robots, d_grf0, d_grf_full, d_status,
                   d_resid, d_info, nullptr, d_warm, d_order, (cudaStream_t)stream);
 }
 
 int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_records,
-                              const float* h_robot_params, const int32_t* h_robot_type, int n_robots,
+                              const float* h_robot_params, const int32_t* h_robot_type, int n_types, int n_robots,
                               float* h_grf0, float* h_grf_full, int32_t* h_status) {
   int rc = check_settings(settings);
   if (rc) return rc;
-  if (!h_records || !h_robot_params || !h_grf0 || n_robots < 0) {
-    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+  if (!h_records || !h_robot_params || !h_grf0 || n_robots < 0 || n_types < 1) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch / n_types < 1");
     return MPC_B200_EINVAL;
   }
+  if (h_robot_type)
+    for (int i = 0; i < n_robots; ++i)
+      if (h_robot_type[i] < 0 || h_robot_type[i] >= n_types) {
+        snprintf(g_err, sizeof(g_err), "robot_type[%d] = %d outside [0, %d)", i, h_robot_type[i], n_types);
+        return MPC_B200_EINVAL;
+      }
   if (mpc_b200_device_count() <= 0) {
     snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
     return MPC_B200_ENOGPU;
   }
   if (n_robots == 0) return MPC_B200_OK;
   const int h = settings->horizon;
-  int n_types = 1;
-  if (h_robot_type)
-    for (int i = 0; i < n_robots; ++i) n_types = h_robot_type[i] + 1 > n_types ? h_robot_type[i] + 1 : n_types;
   const size_t b_rec = align256((size_t)n_robots * MPC_REC_STRIDE(h) * 4);
   const size_t b_rp = align256((size_t)n_types * MPC_ROBOT_PARAMS_STRIDE * 4);
   const size_t b_rt = align256((size_t)n_robots * 4);
@@ -461,7 +507,7 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_re
   CK(cudaMemcpyAsync(d_rp, h_robot_params, (size_t)n_types * MPC_ROBOT_PARAMS_STRIDE * 4,
                      cudaMemcpyHostToDevice, st));
   if (h_robot_type) CK(cudaMemcpyAsync(d_rt, h_robot_type, (size_t)n_robots * 4, cudaMemcpyHostToDevice, st));
-  rc = dispatch(settings, d_rec, d_rp, h_robot_type ? d_rt : nullptr, n_robots, d_g0,
+  rc = dispatch(settings, d_rec, d_rp, h_robot_type ? d_rt : nullptr, n_types, n_robots, d_g0,
                 h_grf_full ? d_gf : nullptr, h_status ? d_st : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                 st);
   if (rc) return rc;
@@ -474,19 +520,32 @@ int mpc_b200_solve_batch_host(const MpcB200Settings* settings, const float* h_re
 
 int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick, const float* d_dof,
                   const float* d_body, const float* d_est, const float* d_cmd, int has_weights,
-                  const int32_t* d_gait,
-                  const float* d_robot_params, const float* d_robot_geom, const int32_t* d_robot_type,
-                  int n_robots, float* d_state, float* d_torques, float* d_grf0, float* d_records,
-                  int32_t* d_solved, double* d_warm, const int32_t* d_order, void* stream) {
+                  const float* d_actions, const int32_t* d_gait,
+                  const float* d_robot_params, const float* d_robot_geom, const int32_t* d_robot_type, int n_types,
+                  int n_robots, const int32_t* d_active, float* d_state, float* d_torques, float* d_grf0,
+                  float* d_records, int32_t* d_solved, double* d_warm, const int32_t* d_order, void* stream) {
   int rc = check_settings(settings);
   if (rc) return rc;
   if (!tick || tick->iters_between_mpc <= 0 || !(tick->dt > 0)) {
     snprintf(g_err, sizeof(g_err), "invalid tick parameters");
     return MPC_B200_EINVAL;
   }
-  if (n_robots < 0 || (n_robots > 0 && (!d_dof || (!d_est == !d_body) || !d_cmd || !d_robot_params ||
-                                        !d_robot_geom || !d_state || !d_torques))) {
-    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+  if (n_robots < 0 || n_types < 1 || (n_robots > 0 && (!d_dof || (!d_est == !d_body) || !d_cmd || !d_robot_params ||
+                                                       !d_robot_geom || !d_state || !d_torques))) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch / n_types < 1");
+    return MPC_B200_EINVAL;
+  }
+  const int cstride = tick->cmd_stride > 0 ? tick->cmd_stride : MPC_CMD_STRIDE;
+  if (cstride != 3 && cstride != MPC_CMD_STRIDE) {
+    snprintf(g_err, sizeof(g_err), "cmd_stride must be 3 or %d", MPC_CMD_STRIDE);
+    return MPC_B200_EINVAL;
+  }
+  if (has_weights && !d_actions && cstride != MPC_CMD_STRIDE) {
+    snprintf(g_err, sizeof(g_err), "has_weights needs cmd_stride == %d (or pass d_actions)", MPC_CMD_STRIDE);
+    return MPC_B200_EINVAL;
+  }
+  if (d_active && !d_body) {
+    snprintf(g_err, sizeof(g_err), "d_active (FSM gate with locomotionSafe) needs d_body");
     return MPC_B200_EINVAL;
   }
   if (mpc_b200_device_count() <= 0) {
@@ -503,12 +562,19 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
   tp.iters_between_mpc = tick->iters_between_mpc;
   tp.flat_ground = tick->flat_ground;
   tp.bonus_swing = tick->bonus_swing;
+  tp.cmd_stride = cstride;
+  for (int i = 0; i < 12; ++i) {
+    tp.act_scale[i] = tick->act_scale[i];
+    tp.act_const[i] = tick->act_const[i];
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (settings->horizon == 10)
-    return launch_tick<10>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
-                           d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, d_order, st);
-  return launch_tick<16>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_gait, d_robot_params, d_robot_geom,
-                         d_robot_type, n_robots, d_state, d_torques, d_grf0, d_records, d_solved, d_warm, d_order, st);
+    return launch_tick<10>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_actions, d_gait, d_robot_params,
+                           d_robot_geom, d_robot_type, n_types, n_robots, d_active, d_state, d_torques, d_grf0, d_records,
+                           d_solved, d_warm, d_order, st);
+  return launch_tick<16>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_actions, d_gait, d_robot_params,
+                         d_robot_geom, d_robot_type, n_types, n_robots, d_active, d_state, d_torques, d_grf0, d_records,
+                         d_solved, d_warm, d_order, st);
 }
 
 int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_record,
@@ -530,7 +596,7 @@ int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_reco
   CK(cudaMalloc(&d_dbg, ndbg * 8));
   CK(cudaMemcpy(d_rec, h_record, MPC_REC_STRIDE(h) * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_rp, h_robot_params, MPC_ROBOT_PARAMS_STRIDE * 4, cudaMemcpyHostToDevice));
-  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr, nullptr,
+  rc = dispatch(settings, d_rec, d_rp, nullptr, 1, 1, d_g0, nullptr, nullptr, nullptr, nullptr, d_dbg, nullptr, nullptr,
                 nullptr);
   if (rc == MPC_B200_OK) {
     cudaError_t e = cudaDeviceSynchronize();

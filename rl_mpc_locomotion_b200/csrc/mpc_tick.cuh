@@ -38,7 +38,10 @@ struct TickParams {
   int iters_between_mpc;  // int(27 / (1000 * dt)) = 2, RobotRunnerMin.py:21-22
   int flat_ground;        // Parameters.flat_ground
   float bonus_swing;      // Parameters.cmpc_bonus_swing
-  int reserved[4];
+  int cmd_stride;         // floats per robot in the command tensor: 3 (vx, vy, yaw rate) or 16 (+ 13 weights)
+  int reserved[3];
+  float act_scale[12];    // Parameters.MPC_param_scale  (aliengo.py:237-245: weights = actions * scale + const)
+  float act_const[12];    // Parameters.MPC_param_const
 };
 
 // value rounded through IEEE half precision (numpy float16 storage)
@@ -182,19 +185,12 @@ enum { LG_Q = 0, LG_QD = 3, LG_P = 6, LG_J = 9, LG_V = 18, LG_PFOOT = 21, LG_FOO
        LG_SWING = 28, LG_SWINGTIME = 29, LG_STRIDE = 32 };
 
 // ---------------------------------------------------------------------------------------
-// tick_pre: everything of the tick that precedes the QP solve.  `st` (MPC_TICK_STATE_STRIDE
-// floats, shared memory copy of the robot's persistent state) is updated in place; `rec`
-// receives the QP problem record; returns (uniformly) whether the MPC fires this tick.
+// tick_legs: LegController.updateData (LegController.py:89-106, 135-171) - leg FK, Jacobian, foot
+// velocity, hip-frame foot positions.  Reads the persistent state (CoM height) but does not
+// change it, so the FSM shell's locomotionSafe() check can run between this and tick_pre().
 // ---------------------------------------------------------------------------------------
-template <int H>
-MPC_FN int tick_pre(const float* dof, const float* est, const float* cmd, int has_weights, int gait,
-                    const float* geom, const TickParams& tp, float* st, float* rec, float* legs MPC_LANE_ARG) {
+MPC_FN void tick_legs(const float* dof, const float* geom, const float* st, float* rec, float* legs MPC_LANE_ARG) {
   const float abad = geom[MPC_GEOM_ABAD], hipl = geom[MPC_GEOM_HIP], kneel = geom[MPC_GEOM_KNEE];
-  const float body_h = geom[MPC_GEOM_HEIGHT];
-  const double dt_mpc = (double)tp.dt * tp.iters_between_mpc;
-  int* sti = reinterpret_cast<int*>(st);
-
-  // ---- LegController.updateData (LegController.py:89-106, 135-171)
   LANES_BEGIN
   if (lane < 4) {
     const int leg = lane;
@@ -245,6 +241,21 @@ MPC_FN int tick_pre(const float* dof, const float* est, const float* cmd, int ha
   }
   LANES_END
   WSYNC();
+}
+
+// ---------------------------------------------------------------------------------------
+// tick_pre: everything of the tick between LegController.updateData (tick_legs) and the QP solve.
+// `st` (MPC_TICK_STATE_STRIDE floats, shared memory copy of the robot's persistent state) is
+// updated in place; `rec` receives the QP problem record; returns (uniformly) whether the MPC
+// fires this tick.  `cmd` = vx, vy, yaw rate; `wts` = the 13 MPC weights or null (robot default).
+// ---------------------------------------------------------------------------------------
+template <int H>
+MPC_FN int tick_pre(const float* est, const float* cmd, const float* wts, int gait,
+                    const float* geom, const TickParams& tp, float* st, float* rec, float* legs MPC_LANE_ARG) {
+  const float abad = geom[MPC_GEOM_ABAD];
+  const float body_h = geom[MPC_GEOM_HEIGHT];
+  const double dt_mpc = (double)tp.dt * tp.iters_between_mpc;
+  int* sti = reinterpret_cast<int*>(st);
 
   // ---- first-run init, CoM height, contact history, ground normal (StateEstimator.py:99-144)
   LANES_BEGIN
@@ -362,7 +373,7 @@ MPC_FN int tick_pre(const float* dof, const float* est, const float* cmd, int ha
   const int counter_post = counter + 1;
   LANES_BEGIN
   if (lane == 0) sti[MPC_ST_COUNTER] = counter_post;
-  if (lane < 13) rec[MPC_REC_WEIGHTS + lane] = has_weights ? cmd[3 + lane] : geom[MPC_GEOM_WEIGHTS + lane];
+  if (lane < 13) rec[MPC_REC_WEIGHTS + lane] = wts ? wts[lane] : geom[MPC_GEOM_WEIGHTS + lane];
   if (lane < 3) {
     rec[MPC_REC_COM_POS + lane] = lane == 2 ? st[MPC_ST_POSZ] : 0.0f;
     rec[MPC_REC_COM_VEL + lane] = est[MPC_EST_VBODY + lane];

@@ -83,13 +83,19 @@ def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg
 
 class TickParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("iters_between_mpc", C.c_int), ("flat_ground", C.c_int),
-                ("bonus_swing", C.c_float), ("reserved", C.c_int * 4)]
+                ("bonus_swing", C.c_float), ("cmd_stride", C.c_int), ("reserved", C.c_int * 3),
+                ("act_scale", C.c_float * 12), ("act_const", C.c_float * 12)]
+
+
+ACT_SCALE = (4, 4, 4, 20, 20, 20, 1, 1, 1, 1, 1, 1)     # reference Parameters.MPC_param_scale
+ACT_CONST = (5, 5, 5, 50, 50, 50, 1, 1, 1, 1, 1, 1)     # reference Parameters.MPC_param_const
 
 
 def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robot_type, flat_ground=False,
-         params=None, dt=0.01, iters_between_mpc=2, body=None, warm=None):
+         params=None, dt=0.01, iters_between_mpc=2, body=None, warm=None, actions=None, active=None):
     """One emulated control tick; `state` [N,96] float32 is updated in place.  Pass `body`
-    ([N,13] root states) with est=None to run StateEstimator.update in the emulated kernel."""
+    ([N,13] root states) with est=None to run StateEstimator.update in the emulated kernel;
+    `actions` [N,12] -> weights = actions * scale + const; `active` [N] MPC_TICK_* gate."""
     n = state.shape[0]
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     dof, cmd, rp, geom = f32(dof), f32(cmd), f32(robot_params), f32(robot_geom)
@@ -98,7 +104,11 @@ def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robo
     gait = np.ascontiguousarray(gait, dtype=np.int32)
     rt = np.ascontiguousarray(robot_type, dtype=np.int32)
     assert state.dtype == np.float32 and state.flags.c_contiguous
-    tp = TickParams(dt, iters_between_mpc, int(flat_ground), 0.0)
+    tp = TickParams(dt, iters_between_mpc, int(flat_ground), 0.0, cmd.shape[1])
+    tp.act_scale[:] = ACT_SCALE
+    tp.act_const[:] = ACT_CONST
+    actions = None if actions is None else f32(actions)
+    active = None if active is None else np.ascontiguousarray(active, dtype=np.int32)
     prm = params or default_params()
     torques = np.zeros((n, 12), np.float32)
     grf0 = np.zeros((n, 12), np.float32)
@@ -108,8 +118,10 @@ def tick(state, dof, est, cmd, has_weights, gait, robot_params, robot_geom, robo
     rc = lib().mpc_emu_tick(C.byref(prm), C.byref(tp), P(dof.ctypes.data),
                             P(body.ctypes.data) if body is not None else None,
                             P(est.ctypes.data) if est is not None else None, P(cmd.ctypes.data),
-                            int(has_weights), P(gait.ctypes.data), P(rp.ctypes.data), P(geom.ctypes.data),
-                            P(rt.ctypes.data), n, P(state.ctypes.data), P(torques.ctypes.data), P(grf0.ctypes.data),
+                            int(has_weights), P(actions.ctypes.data) if actions is not None else None,
+                            P(gait.ctypes.data), P(rp.ctypes.data), P(geom.ctypes.data),
+                            P(rt.ctypes.data), n, P(active.ctypes.data) if active is not None else None,
+                            P(state.ctypes.data), P(torques.ctypes.data), P(grf0.ctypes.data),
                             P(records.ctypes.data), P(solved.ctypes.data),
                             P(warm.ctypes.data) if warm is not None else None)
     assert rc == 0

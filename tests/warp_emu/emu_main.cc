@@ -50,8 +50,9 @@ extern "C" int mpc_emu_solve(const float* rec, int n, int horizon, const float* 
 
 // One emulated control tick for n robots (same sequence as mpc_tick_kernel in mpc_b200.cu).
 extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParams* tp, const float* dof,
-                            const float* body, const float* est, const float* cmd, int has_weights, const int* gait,
-                            const float* rp, const float* geom, const int* rt, int n, float* state,
+                            const float* body, const float* est, const float* cmd, int has_weights,
+                            const float* actions, const int* gait,
+                            const float* rp, const float* geom, const int* rt, int n, const int* active, float* state,
                             float* torques, float* grf0, float* records, int32_t* solved, double* warm) {
   constexpr int H = 10;
   using D = mpc::Dims<H>;
@@ -59,7 +60,10 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
   prm.dt = (double)tp->dt * tp->iters_between_mpc;
   std::vector<double> sm(D::SMEM_DOUBLES, 0.0);
   const int stride = MPC_REC_STRIDE(H);
+  const int cstride = tp->cmd_stride > 0 ? tp->cmd_stride : MPC_CMD_STRIDE;
   for (int r = 0; r < n; ++r) {
+    const int gate = active ? active[r] : MPC_TICK_RUN;
+    if (gate == MPC_TICK_SKIP) continue;
     const int type = rt ? rt[r] : 0;
     float rec[stride];
     std::memset(rec, 0, sizeof(rec));
@@ -72,10 +76,29 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
     float est_local[MPC_EST_STRIDE];
     const float* e = est ? est + (size_t)r * MPC_EST_STRIDE : est_local;
     float rp16[2] = {0, 0};
+    float cmd_s[16] = {0};
+    for (int i = 0; i < 16; ++i) {
+      if (i < 3) cmd_s[i] = cmd[(size_t)r * cstride + i];
+      else if (actions) {
+        if (i < 15) {
+          volatile float prod = actions[(size_t)r * 12 + i - 3] * tp->act_scale[i - 3];   // two roundings, no FMA
+          cmd_s[i] = prod + tp->act_const[i - 3];
+        }
+      } else if (has_weights && cstride >= MPC_CMD_STRIDE) cmd_s[i] = cmd[(size_t)r * cstride + i];
+    }
+    const bool with_weights = actions != nullptr || (has_weights && cstride >= MPC_CMD_STRIDE);
     if (!est) mpc::estimator_update(body + (size_t)r * 13, st + MPC_ST_NORMAL, est_local, rp16);
-    const int do_solve = mpc::tick_pre<H>(dof + (size_t)r * 24, e, cmd + (size_t)r * MPC_CMD_STRIDE, has_weights,
-                                          gait ? gait[r] : 0, g, *tp, st, rec, legs);
-    if (!est) reinterpret_cast<int*>(st)[MPC_ST_UNSAFE] = mpc::locomotion_unsafe(rp16, legs + mpc::LG_P, mpc::LG_STRIDE);
+    mpc::tick_legs(dof + (size_t)r * 24, g, st, rec, legs);
+    const int unsafe = est ? 0 : mpc::locomotion_unsafe(rp16, legs + mpc::LG_P, mpc::LG_STRIDE);
+    if (gate == MPC_TICK_CHECK_ONLY || (gate == MPC_TICK_CHECK_RUN && unsafe)) {
+      for (int i = 0; i < 12; ++i) torques[(size_t)r * 12 + i] = 0.0f;
+      reinterpret_cast<int*>(st)[MPC_ST_UNSAFE] = unsafe;
+      if (solved) solved[r] = 0;
+      continue;
+    }
+    const int do_solve = mpc::tick_pre<H>(e, cmd_s, with_weights ? cmd_s + 3 : nullptr, gait ? gait[r] : 0, g, *tp, st,
+                                          rec, legs);
+    if (!est) reinterpret_cast<int*>(st)[MPC_ST_UNSAFE] = unsafe;
     if (records) std::memcpy(records + (size_t)r * stride, rec, sizeof(rec));
     if (do_solve) {
       mpc::fill_tables<H>(sm.data(), prm.dt);
@@ -85,7 +108,8 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
       reinterpret_cast<int*>(st)[MPC_ST_ITERS] = (int)info[mpc::INFO_ITERS];
       if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
     }
-    mpc::tick_post(e, g, (do_solve && st_code == MPC_STATUS_SOLVED) ? grf : nullptr, st, legs, torques + (size_t)r * 12);
+    const bool apply = do_solve && (st_code == MPC_STATUS_SOLVED || st_code == MPC_STATUS_POLISH_OVERFLOW);
+    mpc::tick_post(e, g, apply ? grf : nullptr, st, legs, torques + (size_t)r * 12);
     if (solved) solved[r] = st_code;
   }
   return 0;
