@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py — QP solves/sec of the batched convex-MPC stance-force solver (BASELINE.json).
 
-A "step" is one pass of the hot path over one batch of synthetic problem records
-(BASELINE config 2: 4096 Aliengo, trot, horizon 10; `--workload` selects the others).
+A "step" is one pass of the hot path over one batch of synthetic input:
+  * QP workloads (BASELINE configs 2 / 4): one batched solve of N problem records;
+  * tick workload (config 3): one MPC period of the fused Locomotion tick = `iters_between_mpc` (2)
+    control ticks of N robots driven from Isaac-layout tensors (actions / dof_state / root_states /
+    commands), i.e. exactly one QP solve per robot plus everything around it.
 
-  python bench.py --gpus 1 --steps 20 --warmup 5            # our arm (sm_100a kernel)
-  python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU OSQP path
-  torchrun --nproc-per-node N ... bench.py --gpus N ...     # robots sharded across GPUs
+  python bench.py --gpus 1 --steps 20 --warmup 5                       # our arm (sm_100a kernels)
+  python bench.py --workload tick_mixed_gaits_h10_n2048                # fused tick, config 3 shard
+  python bench.py --impl reference --steps 3 --warmup 1                # the reference's CPU OSQP path
+  torchrun --nproc-per-node N ... bench.py --gpus N ...                # robots sharded across GPUs
 
-One JSON line on stdout (rank 0).  `value` = whole-job QP solves/s with the records resident
-in HBM; `e2e` = the same metric through the C-ABI host entry point (pinned HOST buffers,
-H2D + solve + D2H inside the timed region).  The oracle is used here only as the
-`cpu_baseline` / `--impl reference` leg, never on the measured GPU path.
+One JSON line on stdout (rank 0).  `value` = whole-job QP solves/s with the inputs resident in HBM;
+`e2e` = the same metric through the public entry point with pinned HOST buffers, H2D + compute + D2H
+inside the timed region.  The oracle is used here only as the `cpu_baseline` / `--impl reference`
+leg and to attach GRF errors to the fixed-iteration side measurement, never on the measured path.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -28,12 +33,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (robots per GPU, horizon, gaits, robot types, description)
-    "aliengo_trot_h10_n4096": (4096, 10, (0,), (0,), "4096 Aliengo, trot, horizon 10 (BASELINE config 2)"),
-    "aliengo_mixed_gaits_h10_n2048": (2048, 10, (0, 6, 1), (0,), "2048/GPU Aliengo trot/walk/bound (config 3 shard)"),
-    "mixed_robots_h16_n2048": (2048, 16, (0, 6, 1), (0, 1, 2), "2048/GPU Go1/A1/Aliengo, horizon 16 (config 4 shard)"),
+    # name: (kind, robots per GPU, horizon, gaits, robot types, description)
+    "aliengo_trot_h10_n4096": ("qp", 4096, 10, (0,), (0,), "4096 Aliengo, trot, horizon 10 (BASELINE config 2)"),
+    "aliengo_mixed_gaits_h10_n2048": ("qp", 2048, 10, (0, 6, 1), (0,), "2048/GPU Aliengo trot/walk/bound, QP only (config 3 shard)"),
+    "mixed_robots_h16_n2048": ("qp", 2048, 16, (0, 6, 1), (0, 1, 2), "2048/GPU Go1/A1/Aliengo, horizon 16 (BASELINE config 4 shard)"),
+    "tick_mixed_gaits_h10_n2048": ("tick", 2048, 10, (0, 6, 1), (0,),
+                                   "2048/GPU Aliengo trot/walk/bound, full Locomotion tick from Isaac tensors (BASELINE config 3 shard)"),
 }
 ALGO_BYTES_PER_SOLVE = {10: 468, 16: 564}   # record in + 12 forces + status out
+# fused tick, per robot and MPC period (2 ticks): per tick actions 48 + dof_state 96 + root_states 52 + commands 12
+# + state row 384 in / 384 out + torques 48; once per period the OSQP workspace row (5.1 KB in, 5.1 KB out) when warm
+TICK_BYTES_PER_PERIOD = {"cold": 2 * 1024, "warm": 2 * 1024 + 2 * 642 * 8}
+
+
+def kernel_hash():
+    """Content hash of everything the CUDA library is built from (the .git directory does not travel to
+    the GPU box, so a git hash is not available there)."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rl_mpc_locomotion_b200", "csrc")
+    for f in sorted(os.listdir(d)) + [os.path.join(ROOT, "include", "mpc_b200.h")]:
+        p = f if os.path.isabs(f) else os.path.join(d, f)
+        h.update(open(p, "rb").read())
+    return h.hexdigest()[:12]
 
 
 def load_peaks():
@@ -42,6 +63,42 @@ def load_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cores():
+    """How many worker processes the CPU arm may use: the affinity mask, clipped by the cgroup CPU quota
+    (cpu.max) and by the number of distinct PHYSICAL cores in the mask (SMT siblings share one FP unit:
+    one OSQP process per hyper-thread halves the per-process rate and inflates "cores")."""
+    aff = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    info = {"affinity": len(aff)}
+    quota = None
+    for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(p).read().split()
+            if p.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    info["cgroup_quota"] = quota
+    phys = set()
+    for c in aff:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+            phys.add(sib)
+        except Exception:
+            phys.add(str(c))
+    info["physical"] = len(phys)
+    n = min(len(aff), len(phys))
+    if quota:
+        n = min(n, max(1, int(quota)))
+    info["used"] = max(1, n)
+    return info
 
 
 class ClockSampler:
@@ -70,6 +127,7 @@ class ClockSampler:
             time.sleep(0.004)
 
     def start(self):
+        self.rows, self.stop_flag = [], False
         if self.nv:
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
@@ -92,6 +150,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path = QP builder restatement + the UNMODIFIED reference OSQP (oracle)
+# ---------------------------------------------------------------------------------------------------
 def _oracle_worker(args):
     rec, h, params, rt, mode = args
     from oracle import oracle
@@ -100,24 +161,84 @@ def _oracle_worker(args):
     return time.perf_counter() - t0, int((st == 1).sum())
 
 
-def cpu_reference_rate(rec, rt, params, h, cores, per_worker=192, mode=0):
-    """The reference's CPU path (oracle = builder restatement + UNMODIFIED reference OSQP) on
-    `cores` host processes (OSQP installs a process-global SIGINT handler: processes, not
-    threads).  Every worker solves `per_worker` records taken cyclically from the workload
-    batch (~0.5-1 s of work each); pool start-up and a warm-up call are outside the clock."""
-    import multiprocessing as mp
-    n = len(rec)
-    chunks = []
-    for w in range(cores):
-        idx = (np.arange(per_worker) * cores + w) % n
-        chunks.append((rec[idx], h, params, rt[idx], mode))
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_oracle_worker, [(rec[:4], h, params, rt[:4], mode)] * cores)   # warm the workers
+class CpuArm:
+    """One process per core (OSQP installs a process-global SIGINT handler: processes, not threads).
+    `cold` = fresh OSQP workspace per QP (osqp_setup: AMD ordering + symbolic + numeric factorisation
+    every time - what the reference pays on a ConvexMpc's FIRST call); `warm` = one persistent
+    workspace per process, osqp_update_P_A / update_lin_cost / update_bounds / osqp_solve per QP - the
+    reference's real per-tick path (mpc_osqp.cc:757-780)."""
+
+    def __init__(self, rec, rt, params, h, cores):
+        import multiprocessing as mp
+        self.rec, self.rt, self.params, self.h, self.cores = rec, rt, params, h, cores
+        self.pool = mp.get_context("fork").Pool(cores)
+        self.pool.map(_oracle_worker, [(rec[:4], h, params, rt[:4], 0)] * cores)   # warm the workers
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def run(self, workers, per_worker, mode, offset=0):
+        """-> (solves/s, wall seconds, records solved).  Records are drawn cyclically from the batch."""
+        n = len(self.rec)
+        chunks = []
+        for w in range(workers):
+            idx = (offset + np.arange(per_worker) * workers + w) % n
+            chunks.append((self.rec[idx], self.h, self.params, self.rt[idx], mode))
         t0 = time.perf_counter()
-        pool.map(_oracle_worker, chunks, chunksize=1)
+        res = self.pool.map(_oracle_worker, chunks, chunksize=1)
         wall = time.perf_counter() - t0
-    return cores * per_worker / wall, wall, cores * per_worker
+        return workers * per_worker / wall, wall, workers * per_worker, max(r[0] for r in res)
+
+    def modes(self, per_worker=96):
+        """{1 core, all cores} x {cold, warm} in one table."""
+        out = {}
+        for name, workers, mode in (("1core_cold", 1, 0), ("1core_warm", 1, 1), ("allcores_cold", self.cores, 0),
+                                    ("allcores_warm", self.cores, 1)):
+            v, wall, cnt, _ = self.run(workers, per_worker, mode)
+            out[name] = {"solves_per_s": v, "per_core": v / workers, "workers": workers, "records": cnt, "wall_s": wall}
+        return out
+
+
+def cpu_sample_text(cores_info, per_worker, kind):
+    return (f"{per_worker} records per worker process drawn cyclically from this workload; QP builder = Eigen-free "
+            "restatement of mpc_osqp.cc, solver = the reference's vendored OSQP 0.6.0 compiled unmodified "
+            f"(oracle/_ref), reference settings; `value` = {kind}; workers = {cores_info['used']} "
+            f"(affinity {cores_info['affinity']}, physical cores {cores_info['physical']}, cgroup quota "
+            f"{cores_info['cgroup_quota']})")
+
+
+# ---------------------------------------------------------------------------------------------------
+def tick_inputs(n, seed, sets=8):
+    """Isaac-layout tensors of `sets` consecutive control ticks (kinematic replay around the standing pose;
+    ranges as tests/golden/make_tick_golden.py, commands from cfg/task/Aliengo.yaml:24-27)."""
+    rng = np.random.default_rng(seed)
+    stand = np.tile([0.0, 0.8, -1.6], 4)
+    ph, w0 = rng.uniform(0, 6.28, (n, 12)), rng.uniform(3.0, 9.0, (n, 12))
+    ph_b = rng.uniform(0, 6.28, (n, 3))
+    vx = rng.uniform(-1.0, 1.0, (n, 1))
+    out = []
+    for t in range(sets):
+        tt = 0.01 * t
+        q = stand + 0.12 * np.sin(w0 * tt + ph)
+        qd = 0.12 * w0 * np.cos(w0 * tt + ph)
+        dof = np.stack([q, qd], -1).reshape(n * 12, 2)
+        rpy = np.stack([0.06 * np.sin(3.1 * tt + ph_b[:, 0]), 0.05 * np.sin(2.3 * tt + ph_b[:, 1]),
+                        0.2 * np.sin(0.9 * tt + ph_b[:, 2])], 1)
+        cr, sr, cp, sp = np.cos(rpy[:, 0] / 2), np.sin(rpy[:, 0] / 2), np.cos(rpy[:, 1] / 2), np.sin(rpy[:, 1] / 2)
+        cy, sy = np.cos(rpy[:, 2] / 2), np.sin(rpy[:, 2] / 2)
+        quat = np.stack([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                         cr * cp * cy + sr * sp * sy], 1)
+        root = np.concatenate([np.tile([0.0, 0.0, 0.35], (n, 1)), quat,
+                               np.concatenate([vx + 0.1 * np.sin(2 * tt), 0.05 * np.cos(3 * tt) * np.ones((n, 1)),
+                                               0.02 * np.sin(5 * tt) * np.ones((n, 1))], 1),
+                               np.stack([0.2 * np.sin(4 * tt + ph_b[:, 0]), 0.15 * np.cos(3.3 * tt + ph_b[:, 1]),
+                                         0.3 * np.sin(1.7 * tt + ph_b[:, 2])], 1)], 1)
+        actions = np.clip(rng.uniform(-1, 1, (n, 12)), -1, 1)
+        commands = np.concatenate([vx, rng.uniform(-0.3, 0.3, (n, 1)), rng.uniform(-1.0, 1.0, (n, 1))], 1)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        out.append((f32(actions), f32(dof), f32(root), f32(commands)))
+    return out
 
 
 def main():
@@ -129,42 +250,65 @@ def main():
     ap.add_argument("--workload", default="aliengo_trot_h10_n4096", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="osqp", choices=["osqp", "fixed"])
     ap.add_argument("--admm-iters", type=int, default=50)
+    ap.add_argument("--robots-per-gpu", type=int, default=0, help="override the workload's batch per GPU (sweeps)")
+    ap.add_argument("--tick-cold", action="store_true", help="tick workload: cold OSQP start every MPC tick")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurements (sweeps)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n_per_gpu, h, gaits, robots, desc = WORKLOADS[args.workload]
+    kind, n_per_gpu, h, gaits, robots, desc = WORKLOADS[args.workload]
+    if args.robots_per_gpu > 0:
+        n_per_gpu = args.robots_per_gpu
 
     from rl_mpc_locomotion_b200 import synth
     from rl_mpc_locomotion_b200.robots import RobotType
     # every rank owns its own contiguous shard of robots: seed differs per rank
-    rec, rt, params, _ = synth.make_batch(n_per_gpu, h, seed=1000 + rank, gaits=gaits,
-                                          robot_types=tuple(RobotType(r) for r in robots))
+    rec, rt, params, meta = synth.make_batch(n_per_gpu, h, seed=1000 + rank, gaits=gaits,
+                                             robot_types=tuple(RobotType(r) for r in robots))
+    tick_warm = kind == "tick" and not args.tick_cold
     cfg = {"workload": args.workload, "description": desc, "robots_per_gpu": n_per_gpu, "horizon": h,
            "solver_mode": "osqp-faithful (reference settings, fp64)" if args.mode == "osqp"
            else f"fixed {args.admm_iters} ADMM iterations, no polish",
-           "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"robots sharded x{world}"}
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+           "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"robots sharded x{world}",
+           "kernel_hash": kernel_hash()}
+    if kind == "tick":
+        cfg["step"] = "one MPC period = 2 control ticks (1 QP solve per robot) from Isaac-layout tensors"
+        cfg["osqp_start"] = "warm (persistent per-robot OSQP workspace state, the reference's real per-tick path)" \
+            if tick_warm else "cold (fresh workspace every MPC tick)"
+    cores_info = host_cores()
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        rates, sample = [], 0
-        for _ in range(max(1, min(args.steps, 5))):
-            r, wall, sample = cpu_reference_rate(rec, rt, params, h, cores)
-            rates.append(r)
-        v = float(np.mean(rates))
+        per_worker = 128
+        arm = CpuArm(rec, rt, params, h, cores_info["used"])
+        # the reference's per-tick path is the WARM one (persistent workspace); for the QP-only workloads the
+        # records are independent states, so "warm" means the update path with an unrelated previous iterate
+        mode = 1
+        for i in range(args.warmup):
+            arm.run(cores_info["used"], per_worker, mode, offset=i)
+        walls, cnt = [], 0
+        for i in range(args.steps):
+            v, wall, cnt, _ = arm.run(cores_info["used"], per_worker, mode, offset=7 * i)
+            walls.append(wall)
+        ms = 1e3 * float(np.mean(walls))
+        v = cnt / (ms * 1e-3)
+        table = arm.modes()
+        arm.close()
         line = {"impl": "reference", "metric": "QP solves/sec", "value": v, "unit": "solves/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / v, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                 "sample": f"{sample} records (cyclic draw from the workload) per step; QP builder = Eigen-free "
-                                           "restatement of mpc_osqp.cc, solver = the reference's vendored OSQP "
-                                           "0.6.0 compiled unmodified (oracle/_ref), fresh workspace per QP, "
-                                           f"one process per core ({cores})"},
+                "records_per_step": cnt,
+                "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores_info["used"], "kind": "port",
+                                 "per_core": v / cores_info["used"], "host_cores": cores_info, "modes": table,
+                                 "sample": cpu_sample_text(cores_info, per_worker,
+                                                           "all workers, WARM path (persistent OSQP workspace per process, "
+                                                           "osqp_update_* + osqp_solve = mpc_osqp.cc:757-780)")},
                 "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -172,7 +316,7 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU)
     import torch
     import torch.distributed as dist
-    from rl_mpc_locomotion_b200 import _lib
+    from rl_mpc_locomotion_b200 import _lib, shard
     from rl_mpc_locomotion_b200.batched import BatchedConvexMpc
 
     if not torch.cuda.is_available():
@@ -182,14 +326,37 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     kw = {} if args.mode == "osqp" else dict(mode=_lib.MODE_FIXED, admm_iters=args.admm_iters, polish=0)
-    mpc = BatchedConvexMpc(h, device=dev, robot_params=params, **kw)
-    d_rec = torch.from_numpy(rec).to(dev)
-    d_rt = torch.from_numpy(rt).to(dev)
-    d_out = torch.empty((n_per_gpu, 12), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    launches_per_step = 2
 
-    def step():
-        return mpc.solve(d_rec, d_rt, out=d_out)
+    if kind == "qp":
+        mpc = BatchedConvexMpc(h, device=dev, robot_params=params, **kw)
+        d_rec = torch.from_numpy(rec).to(dev)
+        d_rt = torch.from_numpy(rt).to(dev)
+        d_out = torch.empty((n_per_gpu, 12), dtype=torch.float32, device=dev)
+        state = {}
+
+        def step():
+            state["out"] = mpc.solve(d_rec, d_rt, out=d_out)
+
+        def last_status():
+            return state["out"]["status"], state["out"]["resid"]
+    else:
+        from rl_mpc_locomotion_b200.locomotion import BatchedLocomotion
+        loco = BatchedLocomotion(rt, meta["gait"].astype(np.int32), horizon=h, device=dev, warm_start=tick_warm, **kw)
+        ins = [tuple(torch.from_numpy(a).to(dev) for a in s) for s in tick_inputs(n_per_gpu, 2000 + rank)]
+        per = loco.tick_params.iters_between_mpc
+        launches_per_step = per
+        tcount = [0]
+
+        def step():
+            for _ in range(per):
+                a, d, r, c = ins[tcount[0] % len(ins)]
+                loco.pre_physics_step(a, d, r, c)
+                tcount[0] += 1
+
+        def last_status():
+            return loco.solved, None
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -202,13 +369,14 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     for e0, e1 in ev:
-        flush.fill_(1)           # evict the records / outputs from L2 (outside the timed interval)
+        flush.fill_(1)           # evict the inputs / outputs from L2 (outside the timed interval)
         e0.record()
-        out = step()
+        step()
         e1.record()
     torch.cuda.synchronize()
     ms = float(sum(e0.elapsed_time(e1) for e0, e1 in ev))
-    n_solved = int((out["status"] == 1).sum())
+    st, resid = last_status()
+    n_solved = int((st == 1).sum())
     clocks = sampler.stop() if rank == 0 else None
     tot = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -216,32 +384,74 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)     # device time, max over ranks
     ms_max = float(tot.item())
     value = world * n_per_gpu * args.steps / (ms_max * 1e-3)
+    # the one collective the sharded job may need: per-GPU solve summaries -> one NCCL
+    # all-reduce of 4 doubles, OUTSIDE the timed region
+    fired = st[st != 0]
+    summ = shard.reduce_summary(shard.summarize(fired, resid[st != 0] if resid is not None else None)).tolist()
 
-    # ---- side measurement: the same batch at a FIXED ADMM iteration count (north-star wording;
-    # no termination test / rho adaptation / polish).  Not the headline: it is not what the
-    # reference returns.
-    fixed = None
-    if args.mode == "osqp":
-        mf = BatchedConvexMpc(h, device=dev, robot_params=params, mode=_lib.MODE_FIXED, admm_iters=50, polish=0)
-        for _ in range(3):
-            mf.solve(d_rec, d_rt, out=d_out)
-        torch.cuda.synchronize()
+    # ---- sustained: the same step back to back for >= --sustain-s seconds (clocks / power under load)
+    sustained = None
+    if not args.no_side and args.sustain_s > 0:
+        reps = max(args.steps, int(args.sustain_s / max(ms / args.steps * 1e-3, 1e-6)) + 1)
+        s2 = ClockSampler(local_rank)
+        if rank == 0:
+            s2.start()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(5):
-            mf.solve(d_rec, d_rt, out=d_out)
+        for _ in range(reps):
+            step()
         f1.record()
         torch.cuda.synchronize()
-        fixed = {"admm_iters": 50, "ms_per_step": f0.elapsed_time(f1) / 5,
-                 "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3), "unit": "solves/s",
-                 "note": "fixed 50 ADMM iterations, no termination test / polish (side measurement, rank 0)"}
+        t_s = f0.elapsed_time(f1) * 1e-3
+        tot3 = torch.tensor([t_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(tot3, op=dist.ReduceOp.MAX)
+        sustained = {"value": world * n_per_gpu * reps / float(tot3.item()), "unit": "solves/s", "steps": reps,
+                     "seconds": float(tot3.item()), "l2": "not flushed (back-to-back steps)",
+                     "clocks": s2.stop() if rank == 0 else None}
+
+    # ---- side measurement: the same batch at a FIXED ADMM iteration count (north-star wording; no
+    # termination test / rho adaptation / polish) WITH its accuracy: it is neither what the reference
+    # returns nor the true minimiser, so the error is printed next to the rate.
+    fixed = None
+    if kind == "qp" and args.mode == "osqp" and not args.no_side and rank == 0:
+        fixed = []
+        for k in (25, 50, 100):
+            mf = BatchedConvexMpc(h, device=dev, robot_params=params, mode=_lib.MODE_FIXED, admm_iters=k, polish=0)
+            for _ in range(3):
+                mf.solve(d_rec, d_rt, out=d_out)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(5):
+                mf.solve(d_rec, d_rt, out=d_out)
+            f1.record()
+            torch.cuda.synchronize()
+            row = {"admm_iters": k, "ms_per_step": f0.elapsed_time(f1) / 5,
+                   "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3), "unit": "solves/s"}
+            if not args.no_cpu_baseline:
+                from oracle import oracle
+                ns = min(64, n_per_gpu)
+                if k == 25:
+                    ref0 = oracle.solve_records(rec[:ns], h, params, rt[:ns], mode=oracle.COLD)[0]
+                    tru0 = oracle.solve_records(rec[:ns], h, params, rt[:ns], mode=oracle.TRUE)[0]
+                f = d_out[:ns].cpu().numpy()
+                e_ref, e_tru = np.abs(f - ref0).max(1), np.abs(f - tru0).max(1)
+                row["grf_err_N"] = {"vs_reference_osqp": {"median": float(np.median(e_ref)), "max": float(e_ref.max())},
+                                    "vs_true_minimiser": {"median": float(np.median(e_tru)), "max": float(e_tru.max())},
+                                    "sample": f"first {ns} robots of this batch, horizon-0 forces, oracle on the host"}
+            fixed.append(row)
+        fixed = {"rows": fixed, "note": "fixed K ADMM iterations, no termination test / rho adaptation / polish; side "
+                                        "measurement on rank 0.  NOT the reference's answer: see grf_err_N"}
 
     # ---- side measurement: the headline solve again, launched longest-first using the iteration
     # counts of a previous solve of the same robots (the d_order scheduling hint; identical results).
     lpt = None
-    if args.mode == "osqp":
+    if kind == "qp" and args.mode == "osqp" and not args.no_side and rank == 0:
         from rl_mpc_locomotion_b200.batched import lpt_order
-        order = lpt_order(mpc.solve(d_rec, d_rt, info=True)["info"])
+        info = mpc.solve(d_rec, d_rt, info=True)["info"]
+        order = lpt_order(info)
         for _ in range(3):
             mpc.solve(d_rec, d_rt, out=d_out, order=order)
         torch.cuda.synchronize()
@@ -251,15 +461,42 @@ def main():
             mpc.solve(d_rec, d_rt, out=d_out, order=order)
         f1.record()
         torch.cuda.synchronize()
+        it = info[:, 0].cpu().numpy()
         lpt = {"ms_per_step": f0.elapsed_time(f1) / 5, "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3),
-               "unit": "solves/s",
+               "unit": "solves/s", "osqp_iterations": {"mean": float(it.mean()), "median": float(np.median(it)),
+                                                       "max": float(it.max())},
                "note": "same OSQP-faithful solve, CTAs launched in descending order of the previous solve's "
                        "iteration counts (perfect prediction here because the batch repeats; side measurement, rank 0)"}
 
-    # ---- e2e: C-ABI host entry point, pinned host buffers, copies inside the timed region
-    from rl_mpc_locomotion_b200.batched import solve_host_pinned
+    # ---- e2e: the public entry point fed from pinned HOST buffers, copies inside the timed region
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_s, h2d, d2h = solve_host_pinned(rec, rt, params, h, e2e_steps, warmup=2, **kw)
+    if kind == "qp":
+        from rl_mpc_locomotion_b200.batched import solve_host_pinned
+        e2e_s, h2d, d2h = solve_host_pinned(rec, rt, params, h, e2e_steps, warmup=2, **kw)
+        e2e_api = "mpc_b200_solve_batch_host (C-ABI, pinned host buffers)"
+    else:
+        host = [tuple(torch.from_numpy(a).pin_memory() for a in s) for s in tick_inputs(n_per_gpu, 2000 + rank)]
+        dbuf = [torch.empty_like(t, device=dev) for t in host[0]]
+        tq = torch.empty((n_per_gpu, 12), dtype=torch.float32).pin_memory()
+
+        def e2e_step(i):
+            for k in range(per):
+                for dst, src in zip(dbuf, host[(per * i + k) % len(host)]):
+                    dst.copy_(src, non_blocking=True)
+                tau = loco.pre_physics_step(*dbuf)
+                tq.copy_(tau, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for i in range(2):
+            e2e_step(i)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        e2e_s = time.perf_counter() - t0
+        h2d = per * sum(t.numel() * 4 for t in host[0])
+        d2h = per * tq.numel() * 4
+        e2e_api = ("BatchedLocomotion.pre_physics_step (mpc_b200_tick): actions / dof_state / root_states / commands "
+                   "from pinned host tensors every tick, torques back to pinned host memory every tick")
     tot2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
@@ -272,43 +509,65 @@ def main():
         return
     peak, peak_src = load_peaks()
     kernel_ms = ms_max / args.steps
-    algo_bytes = ALGO_BYTES_PER_SOLVE[h] * n_per_gpu
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic, smem_frac = None, None
+    if kind == "qp":
+        algo_bytes = ALGO_BYTES_PER_SOLVE[h] * n_per_gpu
+        per_launch_ms = kernel_ms                  # the overflow instantiation exits at once (~3 us)
+        dominant = f"mpc_solve_kernel<{h},...>"
+    else:
+        algo_bytes = TICK_BYTES_PER_PERIOD["warm" if tick_warm else "cold"] * n_per_gpu
+        per_launch_ms = kernel_ms                  # bytes and time are both per MPC period (2 launches)
+        dominant = f"mpc_tick_kernel<{h},{'true' if tick_warm else 'false'}> (per MPC period = 2 launches)"
+    achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+    # ncu-derived figures are a CITATION of a capture, valid only for the kernel they were taken on: they
+    # carry the kernel hash of that capture and are dropped when it differs from this build
+    traffic, binding = None, None
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tp):
         try:
             prof = json.load(open(tp)).get(args.workload, {})
-            traffic, smem_frac = prof.get("dram_bytes_per_launch"), prof.get("smem_pipe_frac_of_peak")
+            if prof.get("kernel_hash") == cfg["kernel_hash"]:
+                traffic = prof.get("dram_bytes_per_launch")
+                binding = {"name": prof.get("binding_roof", "shared-memory bandwidth (l1tex lsu shared wavefronts)"),
+                           "frac_of_peak": prof.get("binding_frac_of_peak"), "captured_on_kernel_hash": prof.get("kernel_hash"),
+                           "source": prof.get("source", "ncu --set full capture summarised in profiles/")}
+            else:
+                binding = {"name": None, "frac_of_peak": None,
+                           "note": f"profiles/dram_traffic.json was captured on kernel {prof.get('kernel_hash')}, this build is "
+                                   f"{cfg['kernel_hash']}: not quoted"}
         except Exception:
             traffic = None
     line = {"metric": "QP solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "solved_fraction": n_solved / n_per_gpu,
-            # per step: the solve kernel + the (10 us, all CTAs exit) polish-overflow instantiation
-            "gpu_launches": 2 * args.steps, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "summary_all_ranks": {"n_solved": summ[0], "n_not_solved": summ[1], "max_pri_res": summ[2],
+                                  "max_dua_res": summ[3], "collective": "nccl all_reduce (4 doubles)" if world > 1 else "none (1 rank)"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mpc_b200_solve_batch_host (C-ABI, pinned host buffers)"},
+                    "steps": e2e_steps, "api": e2e_api},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "binding_roof": {"name": "shared-memory bandwidth (l1tex lsu shared wavefronts)",
-                                          "frac_of_peak": smem_frac,
-                                          "source": "ncu --set full capture summarised in profiles/"},
-                         "note": "algorithmic HBM traffic is ~0.5 KB/solve, so the HBM fraction is tiny by "
-                                 "construction; the binding limits of this fp64 warp-per-robot kernel are "
+                         "traffic": traffic, "peak_source": peak_src, "kernel": dominant,
+                         "algorithmic_bytes_per_step": algo_bytes, "binding_roof": binding,
+                         "note": "algorithmic HBM traffic is 0.5-12 KB per solve, so the HBM fraction is tiny by "
+                                 "construction; the binding limits of this fp64 CTA-per-robot kernel are "
                                  "instruction issue/latency and shared-memory bandwidth (DESIGN.md §7)"}}
+    if kind == "tick":
+        line["robot_ticks_per_s"] = value * launches_per_step
+    if sustained is not None:
+        line["sustained"] = sustained
     if fixed is not None:
         line["fixed_iteration_mode"] = fixed
     if lpt is not None:
         line["longest_first_launch_order"] = lpt
     if not args.no_cpu_baseline:
-        v, wall, sample = cpu_reference_rate(rec, rt, params, h, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} records drawn cyclically from this workload, one pass ({wall:.1f} s wall); QP "
-                                          "builder restatement + the reference's vendored OSQP 0.6.0 compiled "
-                                          "unmodified (oracle/_ref), reference settings, fresh workspace per QP, "
-                                          f"one process per core"}
+        arm = CpuArm(rec, rt, params, h, cores_info["used"])
+        table = arm.modes(per_worker=64)
+        arm.close()
+        best = table["allcores_warm"]
+        line["cpu_baseline"] = {"value": best["solves_per_s"], "unit": "solves/s", "cores": cores_info["used"], "kind": "port",
+                                "per_core": best["per_core"], "host_cores": cores_info, "modes": table,
+                                "sample": cpu_sample_text(cores_info, 64, "all workers, WARM path (persistent OSQP workspace "
+                                                                          "per process = mpc_osqp.cc:757-780)")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -289,6 +289,12 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
                   float* d_grf0, float* d_records, int32_t* d_solved, double* d_warm,
                   const int32_t* d_order, void* stream);
 
+/* Debug / test hook: StateEstimator.update (StateEstimator.py:57-97) alone on the device, exactly the
+ * function the tick kernel runs when d_body is given.  h_body [n,13] root states, h_normal [n,3] the
+ * previous tick's ground normal (yaw frame), h_est [n, MPC_EST_STRIDE] out.  Host pointers; synchronises.
+ * The parity tests compare rpyBody and ground_R_body_frame (float16 in the reference) BIT FOR BIT.      */
+int mpc_b200_debug_estimator(const float* h_body, const float* h_normal, float* h_est, int n);
+
 /* Debug / test hook: run ONE record through the solve kernel and copy back the
  * quantities the kernel never materialises in production: the dense Hessian
  * P[n*n] (row-major, n = 12h) and gradient q[n] of the condensed QP

@@ -76,7 +76,7 @@ def constraints(mass, h, kw):
     return C, l.reshape(-1), u.reshape(-1)
 
 
-def build_qp_literal(mass, inertia9, h, dt, alpha, **kw):
+def build_qp_literal(mass, inertia9, h, dt, alpha, full_a_qp=False, **kw):
     rpy, T, Bw, Bv = _common(mass, inertia9, kw)
     normal = np.asarray(kw["ground_normal_vec"], float)
     A = np.zeros((13, 13))
@@ -93,7 +93,9 @@ def build_qp_literal(mass, inertia9, h, dt, alpha, **kw):
     a_exp, b_exp = Mexp[:13, :13], Mexp[:13, 13:]
     a_qp = np.zeros((13 * h, 13))
     a_qp[:13] = a_exp
-    for i in range(1, h - 1):                                        # :361 (Q1: last block zero)
+    # :361 (Q1): the reference's loop stops at horizon-1, the last a_qp block stays zero.  full_a_qp=True is
+    # the "corrected" builder the reference does NOT implement (tests show the two differ visibly)
+    for i in range(1, h if full_a_qp else h - 1):
         a_qp[13 * i:13 * (i + 1)] = a_exp @ a_qp[13 * (i - 1):13 * i]
     anb = [b_exp]
     for i in range(1, h):

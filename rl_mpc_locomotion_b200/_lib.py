@@ -20,7 +20,7 @@ ACT_SCALE = (4.0, 4.0, 4.0, 20.0, 20.0, 20.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
 ACT_CONST = (5.0, 5.0, 5.0, 50.0, 50.0, 50.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
 EXPORTS = ("mpc_b200_default_settings", "mpc_b200_version", "mpc_b200_last_error",
            "mpc_b200_device_count", "mpc_b200_kernel_info", "mpc_b200_solve_batch",
-           "mpc_b200_solve_batch_host", "mpc_b200_debug_build_qp", "mpc_b200_tick")
+           "mpc_b200_solve_batch_host", "mpc_b200_debug_build_qp", "mpc_b200_debug_estimator", "mpc_b200_tick")
 
 
 class MpcB200Error(RuntimeError):
@@ -79,6 +79,8 @@ def lib():
         L.mpc_b200_solve_batch_host.restype = C.c_int
         L.mpc_b200_debug_build_qp.argtypes = [C.POINTER(Settings), vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_debug_build_qp.restype = C.c_int
+        L.mpc_b200_debug_estimator.argtypes = [vp, vp, vp, C.c_int]
+        L.mpc_b200_debug_estimator.restype = C.c_int
         L.mpc_b200_tick.argtypes = [C.POINTER(Settings), C.POINTER(TickParams), vp, vp, vp, vp, C.c_int, vp, vp, vp, vp,
                                     vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tick.restype = C.c_int

@@ -248,6 +248,13 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
   if (solved && lane == 0) solved[robot] = stat_s[0];
 }
 
+// StateEstimator.update alone (debug / parity hook): one thread per robot
+__global__ void estimator_kernel(const float* __restrict__ body, const float* __restrict__ normal,
+                                 float* __restrict__ est, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) mpc::estimator_update(body + (size_t)r * 13, normal + (size_t)r * 3, est + (size_t)r * MPC_EST_STRIDE);
+}
+
 template <int H>
 int launch_tick(const mpc::SolveParams& prm, const mpc::TickParams& tp, const float* dof, const float* body,
                 const float* est, const float* cmd, int has_weights, const float* actions, const int32_t* gait,
@@ -575,6 +582,35 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
   return launch_tick<16>(prm, tp, d_dof, d_body, d_est, d_cmd, has_weights, d_actions, d_gait, d_robot_params,
                          d_robot_geom, d_robot_type, n_types, n_robots, d_active, d_state, d_torques, d_grf0, d_records,
                          d_solved, d_warm, d_order, st);
+}
+
+int mpc_b200_debug_estimator(const float* h_body, const float* h_normal, float* h_est, int n) {
+  if (!h_body || !h_normal || !h_est || n < 0) {
+    snprintf(g_err, sizeof(g_err), "null pointer / negative batch");
+    return MPC_B200_EINVAL;
+  }
+  if (mpc_b200_device_count() <= 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: this library has no CPU path");
+    return MPC_B200_ENOGPU;
+  }
+  if (n == 0) return MPC_B200_OK;
+  float *d_body = nullptr, *d_normal = nullptr, *d_est = nullptr;
+  CK(cudaMalloc(&d_body, (size_t)n * 13 * 4));
+  CK(cudaMalloc(&d_normal, (size_t)n * 3 * 4));
+  CK(cudaMalloc(&d_est, (size_t)n * MPC_EST_STRIDE * 4));
+  int rc = MPC_B200_OK;
+  cudaError_t e = cudaMemcpy(d_body, h_body, (size_t)n * 13 * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_normal, h_normal, (size_t)n * 3 * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    estimator_kernel<<<(n + 63) / 64, 64>>>(d_body, d_normal, d_est, n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h_est, d_est, (size_t)n * MPC_EST_STRIDE * 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) rc = cuda_fail(e, "debug estimator");
+  cudaFree(d_body);
+  cudaFree(d_normal);
+  cudaFree(d_est);
+  return rc;
 }
 
 int mpc_b200_debug_build_qp(const MpcB200Settings* settings, const float* h_record,

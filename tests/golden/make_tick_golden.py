@@ -37,7 +37,7 @@ def quat_xyzw(roll, pitch, yaw):
     return np.array([x, y, z, w])
 
 
-def run_case(name, robot, gait, flat, ticks, seed, with_weights):
+def run_case(name, robot, gait, flat, ticks, seed, with_weights, compact=False):
     rng = np.random.default_rng(seed)
     Parameters.cmpc_gait = gait
     Parameters.flat_ground = flat
@@ -104,11 +104,25 @@ def run_case(name, robot, gait, flat, ticks, seed, with_weights):
             log["qp_args"].append(np.zeros(96)); log["qp_out"].append(np.zeros(120))
     out = {k: np.asarray(v) for k, v in log.items()}
     out["meta"] = np.array([int(robot.value), int(gait.value), int(flat), int(with_weights)])
+    if compact:   # long replays: float32 storage (every logged quantity is float32 / float16 in the reference
+        # except the solver's float64 output, whose float32 rounding is 4e-6 N), QP data only on MPC ticks
+        sel = out["solved"].astype(bool)
+        out = {"dof": out["dof"].astype(np.float32), "body": out["body"].astype(np.float32),
+               "cmd": out["cmd"].astype(np.float32), "torques": out["torques"].astype(np.float32),
+               "counter": out["counter"].astype(np.int32), "solved": sel, "z_post": out["z_post"].astype(np.float32),
+               "contact_phase": out["contact_phase"].astype(np.float32), "f_ff": out["f_ff"].astype(np.float32),
+               "qp_args": out["qp_args"][sel].astype(np.float32), "qp_out": out["qp_out"][sel].astype(np.float32),
+               "meta": out["meta"]}
     np.savez_compressed(os.path.join(HERE, f"tick_golden_{name}.npz"), **out)
     print(name, "ticks", ticks, "qp solves", int(out["solved"].sum()), "max |tau|", np.abs(out["torques"]).max())
 
 
 if __name__ == "__main__":
+    if "--config1" in sys.argv:   # BASELINE config 1: 1 Aliengo, trot, h = 10, 1000 ticks of RobotRunnerMin with
+        # the reference's persistent OSQP workspace (run with --warm --config1)
+        assert "--warm" in sys.argv
+        run_case("config1_aliengo_trot_warm_1000", RobotType.ALIENGO, GaitType.TROT, False, 1000, 11, True, compact=True)
+        sys.exit(0)
     if "--warm" in sys.argv:   # the reference's persistent OSQP workspace (warm start every tick)
         run_case("aliengo_trot_warm", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True)
         sys.exit(0)

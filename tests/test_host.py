@@ -77,7 +77,7 @@ def test_no_cpu_fallback():
         solve_host(rec, 10, robot_params=params, robot_type=rt)
     with pytest.raises(_lib.MpcB200Error):
         _lib.check(_lib.lib().mpc_b200_solve_batch(C.byref(_lib.default_settings(horizon=12)), None, None, None,
-                                                   0, None, None, None, None, None, None, None, None), "bad horizon")
+                                                   1, 0, None, None, None, None, None, None, None, None), "bad horizon")
 
 
 def test_product_does_not_import_oracle():
@@ -87,3 +87,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", "") or f in ("synth.py",), f
+
+
+def test_host_entry_rejects_bad_robot_type_before_touching_the_gpu():
+    """Argument validation of the C-ABI happens on the host, before the device probe: a robot_type
+    outside [0, n_types) or n_types < 1 is MPC_B200_EINVAL (device-pointer entry points flag the
+    robot with MPC_STATUS_BAD_INDEX instead, tests/test_gpu_parity.py)."""
+    from rl_mpc_locomotion_b200.batched import solve_host
+    rec, rt, params, _ = synth.make_batch(3, 10, seed=0)
+    bad = rt.copy()
+    bad[1] = 7
+    with pytest.raises(_lib.MpcB200Error, match=r"robot_type\[1\] = 7 outside"):
+        solve_host(rec, 10, robot_params=params, robot_type=bad)
+    tp = _lib.tick_params(cmd_stride=5)
+    s = _lib.default_settings()
+    one = C.c_void_p(8)   # never dereferenced: validation fails first
+    rc = _lib.lib().mpc_b200_tick(C.byref(s), C.byref(tp), one, one, None, one, 0, None, None, one, one, None, 3, 4,
+                                  None, one, one, None, None, None, None, None, None)
+    assert rc == -1 and b"cmd_stride" in _lib.lib().mpc_b200_last_error()
+
+
+def test_no_reference_gait_can_overflow_the_tick_kernels_polish_buffer():
+    """The fused tick has no polish-overflow pass (include/mpc_b200.h, MPC_STATUS_POLISH_OVERFLOW):
+    its polish buffer holds 6h free coordinates = 2h stance leg-steps with all three force
+    components free.  Every gait of the reference (ConvexMPCLocomotion.py:30-56), at every solve
+    phase, for both built horizons, must stay within that."""
+    for h in (10, 16):
+        for gid in gait.GAITS:
+            for k in range(10):
+                table = gait.mpc_table(gid, k + 0.5, h)
+                assert table.sum() <= 2 * h, (h, gid, k, table.sum())
