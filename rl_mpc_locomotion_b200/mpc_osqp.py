@@ -17,8 +17,9 @@ State across calls, as in the reference object:
   include/mpc_b200.h).  The first call is ``osqp_setup`` + cold solve, every later call is the
   reference's ``osqp_update_P_A`` / ``update_lin_cost`` / ``update_bounds`` / warm-started
   ``osqp_solve`` (mpc_osqp.cc:757-780): warm x / y, the adapted rho, and the cost scaling that still
-  sees the previous q.  ``reset_solver()`` sets the reference's ``initial_run_`` (mpc_osqp.cc:576):
-  the next call sets the workspace up from scratch again.
+  sees the previous q.  ``reset_solver()`` only sets the reference's ``initial_run_`` flag
+  (mpc_osqp.cc:576), which the OSQP branch never reads (it tests ``workspace_ == 0``,
+  mpc_osqp.cc:757): the workspace survives, as here.  A new ``ConvexMpc`` object starts cold.
 * ``QPOASES`` (what the reference's Python passes, ConvexMPCLocomotion.py:108): the reference's
   qpOASES branch (mpc_osqp.cc:797-947, source absent from the checkout) is an active-set solver
   that returns the QP's unique minimiser, cold, on every call.  The north-star forbids dispatching
@@ -110,7 +111,7 @@ class ConvexMpc:
             return []                                         # mpc_osqp.cc:791-794
         return out["grf_full"][0].tolist()
 
-    def reset_solver(self):                                   # mpc_osqp.cc:576: initial_run_ = true
-        if self._warm is not None:
-            self._warm.zero_()
+    def reset_solver(self):
+        """mpc_osqp.cc:576: ``initial_run_ = true`` and nothing else - the OSQP branch keys on
+        ``workspace_ == 0`` (:757), so the persistent workspace (here: ``_warm``) is NOT dropped."""
         return None

@@ -104,6 +104,8 @@ def run_case(name, robot, gait, flat, ticks, seed, with_weights, compact=False):
             log["qp_args"].append(np.zeros(96)); log["qp_out"].append(np.zeros(120))
     out = {k: np.asarray(v) for k, v in log.items()}
     out["meta"] = np.array([int(robot.value), int(gait.value), int(flat), int(with_weights)])
+    if compact == "return":
+        return out
     if compact:   # long replays: float32 storage (every logged quantity is float32 / float16 in the reference
         # except the solver's float64 output, whose float32 rounding is 4e-6 N), QP data only on MPC ticks
         sel = out["solved"].astype(bool)
@@ -118,10 +120,24 @@ def run_case(name, robot, gait, flat, ticks, seed, with_weights, compact=False):
 
 
 if __name__ == "__main__":
-    if "--config1" in sys.argv:   # BASELINE config 1: 1 Aliengo, trot, h = 10, 1000 ticks of RobotRunnerMin with
-        # the reference's persistent OSQP workspace (run with --warm --config1)
-        assert "--warm" in sys.argv
-        run_case("config1_aliengo_trot_warm_1000", RobotType.ALIENGO, GaitType.TROT, False, 1000, 11, True, compact=True)
+    if "--config1" in sys.argv:   # BASELINE config 1: 1 Aliengo, trot, h = 10, 1000 ticks of RobotRunnerMin, twice:
+        # with a fresh OSQP workspace per solve (cold: every solve is an independent function of its 13
+        # arguments) and with the reference's persistent workspace (warm: what mpc_osqp.cc:757-780 does)
+        runs = {}
+        for mode in ("cold", "warm"):
+            os.environ["MPC_ORACLE_MODE"] = mode       # read by the oracle module's ConvexMpc constructor
+            runs[mode] = run_case("config1", RobotType.ALIENGO, GaitType.TROT, False, 1000, 11, True, compact="return")
+        c, w = runs["cold"], runs["warm"]
+        sel = c["solved"].astype(bool)
+        assert np.array_equal(c["qp_args"], w["qp_args"]) and np.array_equal(sel, w["solved"].astype(bool))
+        f32 = lambda a: np.asarray(a, dtype=np.float32)
+        out = {"dof": f32(c["dof"]), "body": f32(c["body"]), "cmd": f32(c["cmd"]), "counter": c["counter"].astype(np.int32),
+               "solved": sel, "z_post": f32(c["z_post"]), "contact_phase": f32(c["contact_phase"]),
+               "qp_args": f32(c["qp_args"][sel]), "meta": c["meta"],
+               "torques_cold": f32(c["torques"]), "qp_out_cold": f32(c["qp_out"][sel]),
+               "torques_warm": f32(w["torques"]), "qp_out_warm": f32(w["qp_out"][sel])}
+        np.savez_compressed(os.path.join(HERE, "tick_golden_config1_aliengo_trot_1000.npz"), **out)
+        print("config1: 1000 ticks, 500 QP solves, cold + warm outputs")
         sys.exit(0)
     if "--warm" in sys.argv:   # the reference's persistent OSQP workspace (warm start every tick)
         run_case("aliengo_trot_warm", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True)
