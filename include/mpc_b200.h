@@ -81,6 +81,17 @@ extern "C" {
 #define MPC_MODE_FIXED  1  /* same iteration, but exactly `admm_iters` ADMM iterations and no
                               termination test / rho adaptation (BASELINE config 5 sweeps)   */
 
+/* Kernel organisation of mpc_b200_solve_batch (the answers are bit-identical either way):
+ * MONO  = one launch, a robot's whole solve in one CTA (the shipped default);
+ * SPLIT = three code-homogeneous launches (setup + Ruiz scaling | factorisations + ADMM | polish)
+ *         handing robots over through a ~9 KB workspace row each in global memory.  Measured 10 % SLOWER
+ *         than MONO at equal occupancy on B200 (three launch tails instead of one outweigh the
+ *         instruction-cache relief, profiles/r2_experiments.md); kept selectable for experiments.
+ * AUTO  = MONO. */
+#define MPC_PATH_AUTO   0
+#define MPC_PATH_MONO   1
+#define MPC_PATH_SPLIT  2
+
 /* Solver settings.  mpc_b200_default_settings() gives the reference configuration
  * (osqp include/constants.h:59-110 overridden by mpc_osqp.cc:705-712).            */
 typedef struct MpcB200Settings {
@@ -93,7 +104,8 @@ typedef struct MpcB200Settings {
   int   adaptive_rho;   /* osqp ADAPTIVE_RHO (1)                                     */
   int   polish;         /* mpc_osqp.cc:709 (1)                                       */
   int   polish_refine;  /* osqp POLISH_REFINE_ITER (3)                               */
-  int   reserved_i[3];
+  int   kernel_path;    /* MPC_PATH_*: how mpc_b200_solve_batch runs the solve (results identical) */
+  int   reserved_i[2];
   double dt;            /* timestep (mpc_osqp.cc:512), MPC dt = 0.02                 */
   double alpha;         /* force regulariser (mpc_osqp.cc:513), 1e-5                 */
   double rho;           /* osqp RHO 0.1                                              */

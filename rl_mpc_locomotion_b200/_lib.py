@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPC_B200_LIB", os.path.join(_HERE, "libmpc_b200.so"))  # env override: A/B builds
 
 MODE_OSQP, MODE_FIXED = 0, 1
+PATH_AUTO, PATH_MONO, PATH_SPLIT = 0, 1, 2     # MPC_PATH_* (Settings.kernel_path)
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_NON_FINITE, STATUS_POLISH_OVERFLOW, STATUS_BAD_INDEX = 1, -2, -7, -90, -91
 TICK_SKIP, TICK_RUN, TICK_CHECK_RUN, TICK_CHECK_ONLY = 0, 1, 2, 3     # MPC_TICK_* (d_active gate)
 # reference Parameters.MPC_param_scale / MPC_param_const (Parameters.py:25-33)
@@ -31,7 +32,8 @@ class Settings(C.Structure):
     """Mirror of ``MpcB200Settings`` (include/mpc_b200.h)."""
     _fields_ = [("horizon", C.c_int), ("mode", C.c_int), ("admm_iters", C.c_int), ("max_iter", C.c_int),
                 ("check_every", C.c_int), ("scaling_iters", C.c_int), ("adaptive_rho", C.c_int),
-                ("polish", C.c_int), ("polish_refine", C.c_int), ("reserved_i", C.c_int * 3),
+                ("polish", C.c_int), ("polish_refine", C.c_int), ("kernel_path", C.c_int),
+                ("reserved_i", C.c_int * 2),
                 ("dt", C.c_double), ("alpha", C.c_double), ("rho", C.c_double), ("sigma", C.c_double),
                 ("relax", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double),
                 ("delta", C.c_double), ("rho_tol_ratio", C.c_double), ("reserved_d", C.c_double * 3)]

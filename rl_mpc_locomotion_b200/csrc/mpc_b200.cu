@@ -10,6 +10,7 @@
 // returns MPC_B200_ENOGPU.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -64,8 +65,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 #ifndef MPC_MIN_CTAS
-#define MPC_MIN_CTAS 6   // resident robots per SM the register allocation is tuned for (168 regs: no hot-loop spills)
+#define MPC_MIN_CTAS 6   // resident robots per SM the shared-memory-walk build is tuned for (168 regs: no hot-loop spills)
 #endif
+#ifndef MPC_MIN_CTAS_DENSE
+#define MPC_MIN_CTAS_DENSE 4   // h = 10 with M = Hm^-1 in registers: 120 registers of matrix row per lane
+#endif
+template <int H>
+constexpr int min_ctas() { return mpc::Dims<H>::DENSE_M ? MPC_MIN_CTAS_DENSE : MPC_MIN_CTAS; }
 
 template <int H, int PCAP = 6 * H>
 struct KernelCfg {
@@ -83,7 +89,7 @@ struct KernelCfg {
 // table with <= 2H stance leg-steps; robots beyond that leave MPC_STATUS_POLISH_OVERFLOW and are
 // re-solved by the ONLY_OVERFLOW instantiation (PCAP = 12H, larger shared-memory footprint).
 template <int H, bool WARM, int PCAP, bool ONLY_OVERFLOW>
-__global__ void __launch_bounds__(MPC_NL, (PCAP > 6 * H ? 1 : MPC_MIN_CTAS))
+__global__ void __launch_bounds__(MPC_NL, (PCAP > 6 * H ? 1 : min_ctas<H>()))
 mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                  const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type, int n_types,
                  int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
@@ -128,7 +134,72 @@ mpc_solve_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
                       status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
                       info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr,
                       dbg ? dbg + (size_t)robot * dbg_stride : nullptr,
-                      warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
+                      warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, nullptr, lane);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Phase-split batch path: the same solve as mpc_solve_kernel, cut at its two natural seams into three
+// code-homogeneous kernels (SETUP: structure + Ruiz scaling; ADMM: factorisations + iterations;
+// POLISH) that hand each robot over through a ~9 KB workspace row in global memory (L2-resident for
+// a batch).  Why: the monolithic kernel's ~200 KB of SASS is shared by CTAs that sit in different
+// phases (OSQP's iteration counts de-synchronise them), which thrashes the SM's 32 KB instruction
+// cache; per-phase kernels keep each SM in one code region, get a register allocation and a
+// shared-memory footprint of their own (more resident robots in the ADMM phase, which is where the
+// time goes), and only the ADMM kernel's duration depends on the data.  Results are bit-identical
+// to the monolithic kernel (same lane program, tests/test_warp_emu.py::test_phase_split_*).
+// ---------------------------------------------------------------------------------------
+#ifndef MPC_ADMM_CTAS
+#define MPC_ADMM_CTAS 6
+#endif
+template <int PH>
+constexpr int phase_ctas() { return PH == mpc::PH_ADMM ? MPC_ADMM_CTAS : MPC_MIN_CTAS; }
+
+template <int H, bool WARM, int PH>
+__global__ void __launch_bounds__(MPC_NL, phase_ctas<PH>())
+mpc_phase_kernel(const mpc::SolveParams prm, const float* __restrict__ records,
+                 const float* __restrict__ robot_params, const int32_t* __restrict__ robot_type, int n_types,
+                 int n_robots, float* __restrict__ grf0, float* __restrict__ grf_full,
+                 int32_t* __restrict__ status, float* __restrict__ resid, double* __restrict__ info,
+                 double* __restrict__ warm, double* __restrict__ ws_all, const int32_t* __restrict__ order) {
+  using K = KernelCfg<H>;
+  using WL = mpc::WsLayout<H>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  float* rec_s = reinterpret_cast<float*>(smem_raw + K::OFF_REC);
+  float* rp_s = reinterpret_cast<float*>(smem_raw + K::OFF_RP);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + K::OFF_BAR);
+  const int lane = threadIdx.x;
+  if ((int)blockIdx.x >= n_robots) return;
+  const int robot = (PH == mpc::PH_ADMM && order) ? order[blockIdx.x] : (int)blockIdx.x;   // scheduling hint only
+  if (robot < 0 || robot >= n_robots) return;
+  double* const ws = ws_all + (size_t)robot * WL::STRIDE;
+  const int type = robot_type ? robot_type[robot] : 0;
+  if (type < 0 || type >= n_types) {   // bad robot type: reported by the SETUP kernel, skipped by the others
+    if (PH == mpc::PH_SETUP) {
+      if (lane < 12) grf0[(size_t)robot * 12 + lane] = 0.0f;
+      if (grf_full)
+        for (int i = lane; i < 12 * H; i += MPC_NL) grf_full[(size_t)robot * 12 * H + i] = 0.0f;
+      if (status && lane == 0) status[robot] = MPC_STATUS_BAD_INDEX;
+    }
+    return;
+  }
+  if (PH == mpc::PH_ADMM && ws[mpc::WS_STAGE] != mpc::kWsStageAdmm) return;       // uniform per CTA
+  if (PH == mpc::PH_POLISH && ws[mpc::WS_STAGE] != mpc::kWsStagePolish) return;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_load_1d(rec_s, records + (size_t)robot * K::REC_FLOATS, K::REC_BYTES, bar);
+  }
+  if (lane < MPC_ROBOT_PARAMS_STRIDE) rp_s[lane] = robot_params[(size_t)type * MPC_ROBOT_PARAMS_STRIDE + lane];
+  mpc::fill_tables<H>(sm, prm.dt, lane);
+  WSYNC();
+  mbar_wait(bar, 0);
+  mpc::solve_robot<H, WARM, 6 * H, PH>(rec_s, rp_s, prm, sm, grf0 + (size_t)robot * 12,
+                      grf_full ? grf_full + (size_t)robot * 12 * H : nullptr,
+                      status ? status + robot : nullptr, resid ? resid + (size_t)robot * 2 : nullptr,
+                      info ? info + (size_t)robot * mpc::INFO_STRIDE : nullptr, nullptr,
+                      warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, ws, lane);
 }
 
 
@@ -145,7 +216,7 @@ struct TickCfg {
 };
 
 template <int H, bool WARM>
-__global__ void __launch_bounds__(MPC_NL, MPC_MIN_CTAS)
+__global__ void __launch_bounds__(MPC_NL, min_ctas<H>())
 mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const float* __restrict__ dof,
                 const float* __restrict__ body, const float* __restrict__ est, const float* __restrict__ cmd,
                 int has_weights, const float* __restrict__ actions,
@@ -233,7 +304,7 @@ mpc_tick_kernel(const mpc::SolveParams prm, const mpc::TickParams tp, const floa
     mpc::fill_tables<H>(sm, prm.dt, lane);
     __shared__ double info_s[mpc::INFO_STRIDE];
     mpc::solve_robot<H, WARM>(rec_s, rp_s, prm, sm, grf_s, nullptr, stat_s, nullptr, info_s, nullptr,
-                              warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, lane);
+                              warm ? warm + (size_t)robot * MPC_WARM_STRIDE(H) : nullptr, nullptr, lane);
     __syncthreads();
     if (lane == 0) reinterpret_cast<int*>(st_s)[MPC_ST_ITERS] = (int)info_s[mpc::INFO_ITERS];
     if (grf0 && lane < 12) grf0[(size_t)robot * 12 + lane] = grf_s[lane];
@@ -322,6 +393,10 @@ int check_settings(const MpcB200Settings* s) {
     snprintf(g_err, sizeof(g_err), "unknown mode %d", s->mode);
     return MPC_B200_EINVAL;
   }
+  if (s->kernel_path < MPC_PATH_AUTO || s->kernel_path > MPC_PATH_SPLIT) {
+    snprintf(g_err, sizeof(g_err), "unknown kernel_path %d", s->kernel_path);
+    return MPC_B200_EINVAL;
+  }
   if (s->check_every <= 0 || s->max_iter <= 0 || !(s->dt > 0) || !(s->rho > 0)) {
     snprintf(g_err, sizeof(g_err), "invalid settings (check_every/max_iter/dt/rho must be > 0)");
     return MPC_B200_EINVAL;
@@ -332,31 +407,79 @@ int check_settings(const MpcB200Settings* s) {
 template <int H, bool WARM>
 int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int nt, int n, float* grf0,
              float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
-             const int32_t* order, cudaStream_t stream) {
+             const int32_t* order, int path, cudaStream_t stream) {
   using K = KernelCfg<H>;
   using KB = KernelCfg<H, 12 * H>;
+  using WL = mpc::WsLayout<H>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, WARM, 6 * H, false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(mpc_solve_kernel<H, WARM, 12 * H, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, KB::SMEM_BYTES);
+    auto set = [](const void* f, int bytes) {
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set((const void*)mpc_solve_kernel<H, WARM, 6 * H, false>, K::SMEM_BYTES);
+    set((const void*)mpc_solve_kernel<H, WARM, 12 * H, true>, KB::SMEM_BYTES);
+    set((const void*)mpc_phase_kernel<H, WARM, mpc::PH_SETUP>, K::SMEM_BYTES);
+    set((const void*)mpc_phase_kernel<H, WARM, mpc::PH_ADMM>, K::SMEM_BYTES);
+    set((const void*)mpc_phase_kernel<H, WARM, mpc::PH_POLISH>, K::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(max dynamic smem)");
   if (n <= 0) return MPC_B200_OK;
   // the overflow pass needs the per-robot status even when the caller does not want it
   int32_t* st = status;
   if (!st) CK(cudaMallocAsync((void**)&st, (size_t)n * sizeof(int32_t), stream));
-  mpc_solve_kernel<H, WARM, 6 * H, false><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
-                                                                               resid, info, dbg, warm, order);
-  CK(cudaGetLastError());
+  // the phase-split path is opt-in (measured slower than the monolithic kernel, see include/mpc_b200.h);
+  // the debug hook needs the monolithic kernel
+  const bool split = !dbg && path == MPC_PATH_SPLIT;
+  if (split) {
+    // the workspace comes from the device's stream-ordered pool; keep freed blocks in the pool (the
+    // default release threshold of 0 hands them back to the driver at every synchronisation, which
+    // would turn each call's cudaMallocAsync into a fresh 37 MB allocation)
+    static std::once_flag pool_once[64];
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::call_once(pool_once[dev & 63], [dev] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    });
+    double* ws = nullptr;
+    CK(cudaMallocAsync((void**)&ws, (size_t)n * WL::STRIDE * sizeof(double), stream));
+    mpc_phase_kernel<H, WARM, mpc::PH_SETUP><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
+                                                                                  resid, info, warm, ws, nullptr);
+    CK(cudaGetLastError());
+    mpc_phase_kernel<H, WARM, mpc::PH_ADMM><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
+                                                                                 resid, info, warm, ws, order);
+    CK(cudaGetLastError());
+    if (prm.polish) {
+      mpc_phase_kernel<H, WARM, mpc::PH_POLISH><<<n, MPC_NL, K::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full,
+                                                                                     st, resid, info, warm, ws, nullptr);
+      CK(cudaGetLastError());
+    }
+    CK(cudaFreeAsync(ws, stream));
+  } else {
+    // development knob (occupancy experiments): extra dynamic shared memory per CTA
+    static const int extra = [] {
+      const char* e = getenv("MPC_B200_DEBUG_EXTRA_SMEM");
+      const int v = e ? atoi(e) : 0;
+      if (v > 0) cudaFuncSetAttribute((const void*)mpc_solve_kernel<H, WARM, 6 * H, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES + v);
+      return v > 0 ? v : 0;
+    }();
+    mpc_solve_kernel<H, WARM, 6 * H, false><<<n, MPC_NL, K::SMEM_BYTES + extra, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full,
+                                                                                         st, resid, info, dbg, warm, order);
+    CK(cudaGetLastError());
+  }
   // robots whose polish did not fit the fast kernel's buffer (> 2H stance leg-steps): every other
   // CTA of this launch exits at once
-  mpc_solve_kernel<H, WARM, 12 * H, true><<<n, MPC_NL, KB::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
-                                                                               resid, info, dbg, warm, order);
-  CK(cudaGetLastError());
+  if (prm.polish) {
+    mpc_solve_kernel<H, WARM, 12 * H, true><<<n, MPC_NL, KB::SMEM_BYTES, stream>>>(prm, rec, rp, rt, nt, n, grf0, grf_full, st,
+                                                                                 resid, info, dbg, warm, order);
+    CK(cudaGetLastError());
+  }
   if (!status) CK(cudaFreeAsync(st, stream));
   return MPC_B200_OK;
 }
@@ -364,10 +487,10 @@ int launch_w(const mpc::SolveParams& prm, const float* rec, const float* rp, con
 template <int H>
 int launch(const mpc::SolveParams& prm, const float* rec, const float* rp, const int32_t* rt, int nt, int n,
            float* grf0, float* grf_full, int32_t* status, float* resid, double* info, double* dbg, double* warm,
-           const int32_t* order, cudaStream_t stream) {
+           const int32_t* order, int path, cudaStream_t stream) {
   if (warm)
-    return launch_w<H, true>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
-  return launch_w<H, false>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, nullptr, order, stream);
+    return launch_w<H, true>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, path, stream);
+  return launch_w<H, false>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, nullptr, order, path, stream);
 }
 
 int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const int32_t* rt, int nt, int n,
@@ -375,8 +498,8 @@ int dispatch(const MpcB200Settings* s, const float* rec, const float* rp, const 
              const int32_t* order, cudaStream_t stream) {
   const mpc::SolveParams prm = to_params(*s);
   if (s->horizon == 10)
-    return launch<10>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
-  return launch<16>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, stream);
+    return launch<10>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, s->kernel_path, stream);
+  return launch<16>(prm, rec, rp, rt, nt, n, grf0, grf_full, status, resid, info, dbg, warm, order, s->kernel_path, stream);
 }
 
 // grow-only device scratch for the host-pointer convenience entry points
@@ -583,6 +706,18 @@ int mpc_b200_tick(const MpcB200Settings* settings, const MpcB200TickParams* tick
                          d_robot_geom, d_robot_type, n_types, n_robots, d_active, d_state, d_torques, d_grf0, d_records,
                          d_solved, d_warm, d_order, st);
 }
+
+#ifdef MPC_STAGE_TIMING
+int mpc_b200_debug_stage_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_stage_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int mpc_b200_debug_estimator(const float* h_body, const float* h_normal, float* h_est, int n) {
   if (!h_body || !h_normal || !h_est || n < 0) {

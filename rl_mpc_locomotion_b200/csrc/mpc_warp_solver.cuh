@@ -34,6 +34,17 @@
 #include "../../include/mpc_b200.h"
 #include "warp_prog.h"
 
+// Development instrumentation (-DMPC_STAGE_TIMING): cycles between the hand-off points of one ADMM
+// iteration, accumulated by lane 0 of every CTA into a global table (see tools/stage_timing.py).
+#if defined(MPC_STAGE_TIMING) && defined(__CUDACC__) && !defined(MPC_EMULATE)
+__device__ unsigned long long g_stage_cycles[16];
+#define MPC_T0() long long t_stage_ = clock64()
+#define MPC_TICK(slot) do { const long long t_now_ = clock64(); if (lane == 0) atomicAdd(&g_stage_cycles[slot], (unsigned long long)(t_now_ - t_stage_)); t_stage_ = t_now_; } while (0)
+#else
+#define MPC_T0() ((void)0)
+#define MPC_TICK(slot) ((void)0)
+#endif
+
 namespace mpc {
 
 constexpr int NL = MPC_NL;  // threads per robot (1 or 2 warps), see warp_prog.h
@@ -99,6 +110,17 @@ struct Dims {
   // G_k = F_k^-1 U_k ([NW][GS], GS odd: conflict-free rows) lets ksolve() go from s to g = F^-1 U s
   // in one stage.  Only where the extra 6.2 KB do not cost a resident CTA (h = 10: still 6 per SM).
   static constexpr bool FUSE_G = (H <= 10);
+  // EXPERIMENT, off by default (-DMPC_DENSE_M=1): M = Hm^-1 = W^T W held as one dense row per lane IN
+  // REGISTERS (6h <= lanes, i.e. h = 10), so that the ADMM iteration's wrench-space solve is one balanced
+  // 6h-long dot product per lane against a broadcast vector instead of two triangular walks over shared
+  // memory (see factor() / ksolve()).  Measured on B200 (profiles/r2_experiments.md): the per-iteration
+  // latency of a CTA drops from 4336 to 3079 cycles, but the 120 extra registers cap the SM at 4 resident
+  // robots (255 registers, hot-loop spills) and forming M costs as much as the factorisation itself:
+  // 4.96 ms vs 3.55 ms for the 4096-robot OSQP-faithful solve.  Parity-tested, not shipped.
+#ifndef MPC_DENSE_M
+#define MPC_DENSE_M 0
+#endif
+  static constexpr bool DENSE_M = (MPC_DENSE_M != 0) && (NW <= NL) && (NW % 12 == 0);
   static constexpr int GS = 13;
   static constexpr int OFF_G = OFF_DSM + (NV > 2 * PCAP ? NV : 2 * PCAP);
   static constexpr int SMEM_DOUBLES = OFF_G + (FUSE_G ? NW * GS + (NW * GS & 1) : 0);
@@ -403,15 +425,38 @@ MPC_FN void fill_tables(double* sm, double dt
   WSYNC();
 }
 
-template <int H, bool WARM = false, int PCAP_ = 6 * H>
+// Phases of one solve (template mask PH): the monolithic kernels run PH_ALL; the phase-split batch path
+// runs the three phases as three code-homogeneous kernels that hand the robot's state over through a
+// small global-memory workspace row `ws` (WsLayout<H>, ~9 KB at h = 10, L2-resident for a batch):
+//   PH_SETUP   structure + q + Ruiz scaling                      -> ws: c, Wb/Q1'/Q2', per-leg-step q, D, E, contact
+//   PH_ADMM    rho, factorisations, ADMM loop to termination     -> ws: x, z, y, status, iterations, rho, residuals
+//   PH_POLISH  polish (+ acceptance)                             -> outputs
+// Every phase that ends a robot's solve (ADMM when no polish is due, POLISH otherwise) writes the outputs.
+enum { PH_SETUP = 1, PH_ADMM = 2, PH_POLISH = 4, PH_ALL = 7 };
+enum { WS_C = 0, WS_STAGE = 1, WS_STATUS = 2, WS_ITER = 3, WS_RHO = 4, WS_RHO_UPDATES = 5, WS_PRI = 6, WS_DUA = 7, WS_HDR = 8 };
+constexpr double kWsStageAdmm = 1.0, kWsStagePolish = 2.0, kWsStageDone = 3.0;
+template <int H>
+struct WsLayout {
+  using D = Dims<H>;
+  static constexpr int SM_BLOCK = D::OFF_DSM - D::OFF_WB;       // Wb, Q1', Q2' as they sit in shared memory
+  static constexpr int OFF_SM = WS_HDR;
+  static constexpr int OFF_LS = OFF_SM + SM_BLOCK;               // [12][NLS]: q(3) D(3) E(5) contact(1), lane-contiguous
+  static constexpr int OFF_XZY = OFF_LS + 12 * D::NLS;           // [13][NLS]: x(3) z(5) y(5)
+  static constexpr int STRIDE = (OFF_XZY + 13 * D::NLS + 1) & ~1;
+};
+
+template <int H, bool WARM = false, int PCAP_ = 6 * H, int PH = PH_ALL>
 MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& prm, double* sm,
                         float* grf0, float* grf_full, int32_t* status_out, float* resid_out,
-                        double* info_out, double* dbg_out, double* warm
+                        double* info_out, double* dbg_out, double* warm, double* ws
 #if defined(__CUDACC__) && !defined(MPC_EMULATE)
                         , const int lane
 #endif
 ) {
   using D = Dims<H, PCAP_>;
+  using WL = WsLayout<H>;
+  constexpr bool DO_SETUP = (PH & PH_SETUP) != 0, DO_ADMM = (PH & PH_ADMM) != 0, DO_POLISH = (PH & PH_POLISH) != 0;
+  static_assert(PH == PH_ALL || PCAP_ == 6 * H, "the phase-split path uses the fast polish capacity only");
   constexpr int PCAP = D::PCAP;
   // `warm` (MPC_WARM_STRIDE(H) doubles in global memory, or null): OSQP's persistent workspace
   // state between consecutive solves of the same robot (settings.warm_start, mpc_osqp.cc:708,
@@ -483,7 +528,10 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   PER_LANE_ARR(double, xt, [NS][3]);
   PER_LANE(double, red);               // reduction operand
   PER_LANE(double, red2);
+  PER_LANE_ARR(double, mrow, [D::DENSE_M ? NW : 1]);   // row `lane` of M = Hm^-1 (DENSE_M only)
 
+  double cscale = 1.0;  // OSQP's cost scaling c
+  if constexpr (DO_SETUP) {
   // ------------------------------------------------------------------ S1: structure
   LANES_BEGIN
   const int leg = lane & 3;
@@ -738,7 +786,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     LANES_END
   }
 
-  double cscale = 1.0;  // OSQP's cost scaling c
   // column inf-norms of (D P D) WITHOUT the c factor -> vecA   (scaling.c:30-43, lin_alg.c:358)
   // (code size matters more than ILP here: the kernel's phases compete for the instruction cache,
   // so the k loop is kept rolled and the lambda has ONE call site)
@@ -837,6 +884,55 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       LANES_END
       WSYNC();
     }
+  }
+  }  // DO_SETUP
+  if constexpr (DO_SETUP && !DO_ADMM) {   // hand the scaled problem over to the ADMM kernel
+    LANES_BEGIN
+    for (int e = lane; e < WL::SM_BLOCK; e += NL) ws[WL::OFF_SM + e] = sm[D::OFF_WB + e];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + NL * s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          ws[WL::OFF_LS + a * D::NLS + j] = _(qb)[s][a];
+          ws[WL::OFF_LS + (3 + a) * D::NLS + j] = _(Dv)[s][a];
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r) ws[WL::OFF_LS + (6 + r) * D::NLS + j] = _(Ev)[s][r];
+        ws[WL::OFF_LS + 11 * D::NLS + j] = _(cj)[s];
+      }
+    if (lane == 0) {
+      ws[WS_C] = cscale;
+      ws[WS_STAGE] = kWsStageAdmm;
+    }
+    LANES_END
+    return;
+  }
+  if constexpr (!DO_SETUP) {              // ... and pick it up
+    cscale = ws[WS_C];
+    LANES_BEGIN
+    for (int e = lane; e < WL::SM_BLOCK; e += NL) sm[D::OFF_WB + e] = ws[WL::OFF_SM + e];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int j = lane + NL * s;
+      _(valid)[s] = j < D::NLS;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        _(qb)[s][a] = _(valid)[s] ? ws[WL::OFF_LS + a * D::NLS + j] : 0.0;
+        _(Dv)[s][a] = _(valid)[s] ? ws[WL::OFF_LS + (3 + a) * D::NLS + j] : 1.0;
+        _(xv)[s][a] = 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        _(Ev)[s][r] = _(valid)[s] ? ws[WL::OFF_LS + (6 + r) * D::NLS + j] : 1.0;
+        _(zv)[s][r] = 0.0;
+        _(yv)[s][r] = 0.0;
+      }
+      _(cj)[s] = _(valid)[s] ? ws[WL::OFF_LS + 11 * D::NLS + j] : 0.0;
+    }
+    LANES_END
+    WSYNC();
   }
   const double cinv = 1.0 / cscale;
   if (dbg_out) {
@@ -979,10 +1075,38 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     WSYNC();
     cholesky(NW);
     invert_lower(NW);
+    if constexpr (D::DENSE_M) {
+      // M = W^T W, row `lane` into registers: M[i][j] = sum_{k >= max(i,j)} W[k][i] W[k][j].  Rows of W
+      // are visited top to bottom in chunks of 12 so that the unrolled j range is a compile-time
+      // constant per chunk; W[k][j] is a broadcast read, W[k][lane] is contiguous across the lanes.
+      LANES_BEGIN
+      if (lane < NW) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) _(mrow)[j] = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < NW / 12; ++kb) {
+#pragma unroll 1
+          for (int k = 12 * kb; k < 12 * kb + 12; ++k) {
+            if (lane <= k) {
+              const double* const rowk = Wp + tri(k);
+              const double dk = dinv[k];
+              const double wki = (lane == k) ? dk : rowk[lane];
+#pragma unroll
+              for (int j = 0; j < 12 * kb + 12; ++j) {
+                const double wkj = (j < k) ? rowk[j] : (j == k ? dk : 0.0);
+                _(mrow)[j] += wki * wkj;
+              }
+            }
+          }
+        }
+      }
+      LANES_END
+    }
   };
 
   // ksolve(): xt = K^-1 tmp3  (K = Delta + U^T Q U) through the wrench-space system
   auto ksolve = [&]() {
+    MPC_T0();
     LANES_BEGIN
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -999,6 +1123,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
+    MPC_TICK(0);
     if constexpr (D::FUSE_G) {
       LANES_BEGIN  // g = (F^-1 U) s in one stage
       for (int i = lane; i < NW; i += NL) {
@@ -1014,6 +1139,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
       LANES_END
       WSYNC();
+    MPC_TICK(1);
     } else {
       LANES_BEGIN  // t = U s
       for (int i = lane; i < NW; i += NL) {
@@ -1025,6 +1151,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
       LANES_END
       WSYNC();
+    MPC_TICK(2);
       LANES_BEGIN  // g = F^-1 t
       for (int i = lane; i < NW; i += NL) {
         const int k = i / 6, c = i % 6;
@@ -1035,52 +1162,75 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
       LANES_END
       WSYNC();
+    MPC_TICK(3);
     }
-    LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
-    for (int i = lane; i < NW; i += NL) {
-      const double* rowi = Wp + tri(i);
-      double a0 = dinv[i] * vg[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int k = 0;
-      for (; k + 3 < i; k += 4) {
-        const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
-        const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
-        a0 += rowi[k] * g01.x;
-        a1 += rowi[k + 1] * g01.y;
-        a2 += rowi[k + 2] * g23.x;
-        a3 += rowi[k + 3] * g23.y;
+    if constexpr (D::DENSE_M) {
+      LANES_BEGIN  // w = M g: one row of M per lane (registers) against the broadcast g
+      if (lane < NW) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NW; k += 4) {
+          const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+          const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
+          a0 += _(mrow)[k] * g01.x;
+          a1 += _(mrow)[k + 1] * g01.y;
+          a2 += _(mrow)[k + 2] * g23.x;
+          a3 += _(mrow)[k + 3] * g23.y;
+        }
+        vt[lane] = (a0 + a1) + (a2 + a3);
       }
-      if (k < i) {  // last 1..3 columns as one predicated body (no scalar tail loop)
-        const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
-        a0 += rowi[k] * g01.x;
-        if (k + 1 < i) a1 += rowi[k + 1] * g01.y;
-        if (k + 2 < i) a2 += rowi[k + 2] * vg[k + 2];
+      LANES_END
+      WSYNC();
+    MPC_TICK(4);
+    } else {
+      LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
+      for (int i = lane; i < NW; i += NL) {
+        const double* rowi = Wp + tri(i);
+        double a0 = dinv[i] * vg[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 3 < i; k += 4) {
+          const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+          const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
+          a0 += rowi[k] * g01.x;
+          a1 += rowi[k + 1] * g01.y;
+          a2 += rowi[k + 2] * g23.x;
+          a3 += rowi[k + 3] * g23.y;
+        }
+        if (k < i) {  // last 1..3 columns as one predicated body (no scalar tail loop)
+          const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+          a0 += rowi[k] * g01.x;
+          if (k + 1 < i) a1 += rowi[k + 1] * g01.y;
+          if (k + 2 < i) a2 += rowi[k + 2] * vg[k + 2];
+        }
+        vw[i] = (a0 + a1) + (a2 + a3);
       }
-      vw[i] = (a0 + a1) + (a2 + a3);
+      LANES_END
+      WSYNC();
+    MPC_TICK(5);
+      LANES_BEGIN  // w = W^T y (column walk).  All lanes of a warp visit the SAME row i at the same
+      // time (lanes whose column is not yet below the diagonal are predicated off): W[i][c] is then
+      // contiguous across the lanes (no bank conflicts) and y[i] is a broadcast.  A warp issues its
+      // longest column's trip count anyway, so the uniform loop costs no extra steps.
+      static_assert(NW % 4 == 0, "column walk takes rows four at a time");
+      for (int c = lane; c < NW; c += NL) {
+        double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = c & ~31;                       // first column of this warp: a multiple of 4
+        const double* p = Wp + tri(i) + c;     // &W[i][c] (dereferenced only where c < i)
+        for (; i < NW; i += 4) {
+          const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
+          const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
+          if (c < i) a0 += p[0] * y01.x;
+          if (c < i + 1) a1 += p[i + 1] * y01.y;
+          if (c < i + 2) a2 += p[2 * i + 3] * y23.x;
+          if (c < i + 3) a3 += p[3 * i + 6] * y23.y;
+          p += 4 * i + 10;
+        }
+        vt[c] = (a0 + a1) + (a2 + a3);
+      }
+      LANES_END
+      WSYNC();
+    MPC_TICK(6);
     }
-    LANES_END
-    WSYNC();
-    LANES_BEGIN  // w = W^T y (column walk).  All lanes of a warp visit the SAME row i at the same
-    // time (lanes whose column is not yet below the diagonal are predicated off): W[i][c] is then
-    // contiguous across the lanes (no bank conflicts) and y[i] is a broadcast.  A warp issues its
-    // longest column's trip count anyway, so the uniform loop costs no extra steps.
-    static_assert(NW % 4 == 0, "column walk takes rows four at a time");
-    for (int c = lane; c < NW; c += NL) {
-      double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int i = c & ~31;                       // first column of this warp: a multiple of 4
-      const double* p = Wp + tri(i) + c;     // &W[i][c] (dereferenced only where c < i)
-      for (; i < NW; i += 4) {
-        const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
-        const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
-        if (c < i) a0 += p[0] * y01.x;
-        if (c < i + 1) a1 += p[i + 1] * y01.y;
-        if (c < i + 2) a2 += p[2 * i + 3] * y23.x;
-        if (c < i + 3) a3 += p[3 * i + 6] * y23.y;
-        p += 4 * i + 10;
-      }
-      vt[c] = (a0 + a1) + (a2 + a3);
-    }
-    LANES_END
-    WSYNC();
     LANES_BEGIN  // v = g - F^-1 w  -> vecB (NW <= NV)
     for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
@@ -1091,6 +1241,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
+    MPC_TICK(7);
     LANES_BEGIN  // x = s - Delta^-1 U^T v
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -1112,6 +1263,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
     LANES_END
     WSYNC();
+    MPC_TICK(8);
   };
 
   // apply_P(): xt = Pbar * tmp3   (structured mat-vec, used by residuals and polish)
@@ -1177,6 +1329,13 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 
   // ------------------------------------------------------------------ S3: rho, factor
   double rho = fmin(fmax(prm.rho0, kRhoMin), kRhoMax);  // auxil.c:82
+  int iter = 0, status = MPC_STATUS_MAX_ITER, rho_updates = 0;
+  double pri_res = 0, dua_res = 0;
+  PER_LANE_ARR(double, Axv, [NS][5]);
+  PER_LANE_ARR(double, Atyv, [NS][3]);
+  PER_LANE_ARR(double, Pxv, [NS][3]);
+  PER_LANE_ARR(double, nrm, [14]);
+  if constexpr (DO_ADMM) {
   if constexpr (WARM) if (warm_valid) {
     rho = warm[1];   // settings->rho keeps the value adapted during the previous solve
     LANES_BEGIN
@@ -1212,12 +1371,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
 
   // ------------------------------------------------------------------ S4: ADMM
   const double ar = prm.relax, sigma = prm.sigma;
-  int iter = 0, status = MPC_STATUS_MAX_ITER, rho_updates = 0;
-  double pri_res = 0, dua_res = 0;
-  PER_LANE_ARR(double, Axv, [NS][5]);
-  PER_LANE_ARR(double, Atyv, [NS][3]);
-  PER_LANE_ARR(double, Pxv, [NS][3]);
-  PER_LANE_ARR(double, nrm, [14]);
   const int max_iter = prm.fixed_iters > 0 ? prm.fixed_iters : prm.max_iter;
   double rinv_rho = 1.0 / rho, rinv_eq = 1.0 / (kRhoEqFactor * rho);
   int until_check = prm.check_every;
@@ -1228,6 +1381,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       rinv_rho = 1.0 / rho;
       rinv_eq = 1.0 / (kRhoEqFactor * rho);
     }
+    MPC_T0();
     LANES_BEGIN  // rhs = sigma x - q + A^T (rho z - y)      (auxil.c:149-162)
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -1241,7 +1395,9 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
     }
     LANES_END
+    MPC_TICK(12);
     ksolve();
+    { MPC_T0();
     LANES_BEGIN  // update_x, update_z, update_y (auxil.c:188-228)
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -1262,6 +1418,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
     }
     LANES_END
+    MPC_TICK(13); }
     // check_termination every check_every iterations (a countdown instead of iter % check_every)
     const bool check = prm.fixed_iters > 0 ? (iter == max_iter) : (--until_check == 0);
     if (!check) continue;
@@ -1351,10 +1508,76 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     }
   }
   if (iter > max_iter) iter = max_iter;
+  }  // DO_ADMM
+  if constexpr (DO_ADMM && !DO_POLISH) {
+    if (prm.polish && status == MPC_STATUS_SOLVED) {   // the polish kernel finishes this robot
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (_(valid)[s]) {
+          const int j = lane + NL * s;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) ws[WL::OFF_XZY + a * D::NLS + j] = _(xv)[s][a];
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            ws[WL::OFF_XZY + (3 + r) * D::NLS + j] = _(zv)[s][r];
+            ws[WL::OFF_XZY + (8 + r) * D::NLS + j] = _(yv)[s][r];
+          }
+        }
+      if (lane == 0) {
+        ws[WS_STATUS] = status;
+        ws[WS_ITER] = iter;
+        ws[WS_RHO] = rho;
+        ws[WS_RHO_UPDATES] = rho_updates;
+        ws[WS_PRI] = pri_res;
+        ws[WS_DUA] = dua_res;
+        ws[WS_STAGE] = kWsStagePolish;
+      }
+      LANES_END
+      return;
+    }
+    LANES_BEGIN
+    if (lane == 0) ws[WS_STAGE] = kWsStageDone;
+    LANES_END
+  }
+  if constexpr (!DO_ADMM) {
+    if constexpr (WARM) if (warm_valid) {   // the ADMM kernel installed the NEW q (osqp_update_lin_cost); so must we
+      LANES_BEGIN
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (_(valid)[s]) {
+          const int j = lane + NL * s;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) _(qb)[s][a] = (_(Dv)[s][a] * warm[q_new_off + 3 * j + a]) * cscale;
+        }
+      LANES_END
+    }
+    status = (int)ws[WS_STATUS];
+    iter = (int)ws[WS_ITER];
+    rho = ws[WS_RHO];
+    rho_updates = (int)ws[WS_RHO_UPDATES];
+    pri_res = ws[WS_PRI];
+    dua_res = ws[WS_DUA];
+    LANES_BEGIN
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (_(valid)[s]) {
+        const int j = lane + NL * s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) _(xv)[s][a] = ws[WL::OFF_XZY + a * D::NLS + j];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          _(zv)[s][r] = ws[WL::OFF_XZY + (3 + r) * D::NLS + j];
+          _(yv)[s][r] = ws[WL::OFF_XZY + (8 + r) * D::NLS + j];
+        }
+      }
+    LANES_END
+  }
 
   // ------------------------------------------------------------------ S5: polish
   int polish_status = 0, nfree_total = 0;
-  if (prm.polish && status == MPC_STATUS_SOLVED) {
+  const bool polish_due = DO_POLISH && prm.polish && status == MPC_STATUS_SOLVED;
+  if (polish_due) {
     // polish.c:20-95 active-set guess; per leg-step null-space basis of the active rows
     PER_LANE_ARR(double, Yb, [NS][3][3]);   // orthonormal basis: first rk = row space, rest = null space
     PER_LANE_ARR(double, pp, [NS][3]);      // particular (pinned) part of x

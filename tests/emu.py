@@ -52,7 +52,8 @@ def lib():
     return _lib
 
 
-def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg=False, warm=None):
+def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg=False, warm=None, split=False):
+    """`split=True`: the phase-split path (SETUP / ADMM / POLISH as separate calls through the workspace row)."""
     rec = np.ascontiguousarray(records, dtype=np.float32)
     n = rec.shape[0]
     rp = np.ascontiguousarray(robot_params, dtype=np.float32)
@@ -65,6 +66,14 @@ def solve(records, horizon, robot_params, robot_type=None, params=None, want_dbg
     nv = 12 * horizon
     dbg = np.zeros((n, nv + nv * nv + nv + 20 * horizon + 1)) if want_dbg else None
     P = C.c_void_p
+    if split:
+        assert not want_dbg
+        rc = lib().mpc_emu_solve_split(P(rec.ctypes.data), n, horizon, P(rp.ctypes.data),
+                                       P(rt.ctypes.data) if rt is not None else None, C.byref(prm),
+                                       P(grf0.ctypes.data), P(full.ctypes.data), P(status.ctypes.data),
+                                       P(info.ctypes.data), P(warm.ctypes.data) if warm is not None else None)
+        assert rc == 0
+        return dict(grf0=grf0, grf_full=full, status=status, info=info)
     rc = lib().mpc_emu_solve(P(rec.ctypes.data), n, horizon, P(rp.ctypes.data),
                              P(rt.ctypes.data) if rt is not None else None, C.byref(prm),
                              P(grf0.ctypes.data), P(full.ctypes.data), P(status.ctypes.data),

@@ -91,7 +91,8 @@ def test_host_entry_and_dropin_module(oracle_mod):
     ref0, ref_full, st = oracle_mod.solve_records(rec, 10, params, rt, mode=oracle_mod.COLD, full=True)
     assert np.abs(host["grf_full"] - ref_full).max() < TOL_N
     m = ROBOTS[RobotType.ALIENGO]
-    cm = mpc.ConvexMpc(m.mass, list(m.inertia9), 4, 10, 0.02, 1e-5, mpc.QPOASES)
+    # OSQP enum: the first call of a fresh object is osqp_setup + cold solve = the COLD oracle
+    cm = mpc.ConvexMpc(m.mass, list(m.inertia9), 4, 10, 0.02, 1e-5, mpc.OSQP)
     kw = unpack_record(rec[0], 10)
     from rl_mpc_locomotion_b200.mpc_osqp import _ARGS
     forces = cm.compute_contact_forces(*[kw[k] for k in _ARGS])

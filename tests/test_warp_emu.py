@@ -140,3 +140,28 @@ def test_blocked_cholesky_and_inverse_lane_programs(n, pcap):
     Wref = np.linalg.inv(np.linalg.cholesky(A))
     assert np.abs(W - Wref).max() < 1e-12 * np.abs(Wref).max() * n
     assert np.abs(W.T @ W @ A - np.eye(n)).max() < 1e-10
+
+
+def test_phase_split_path_is_bit_identical_to_the_monolithic_kernel():
+    """The opt-in phase-split batch path (SETUP | ADMM | POLISH as three kernels handing a robot over through
+    a global-memory workspace row, MPC_PATH_SPLIT) runs the SAME lane program as the monolithic kernel:
+    outputs, statuses and diagnostics must be bit-identical - cold, over a warm-started sequence, for both
+    horizons, and for contact tables that overflow into the PCAP = 12h kernel.  Every phase is run in a
+    freshly poisoned shared-memory image here, so nothing but the workspace row can cross a kernel boundary."""
+    from rl_mpc_locomotion_b200 import synth
+    from rl_mpc_locomotion_b200.records import REC_CONTACT
+    for h, n in ((10, 48), (16, 12)):
+        rec, rt, params, _ = synth.make_batch(n, h, seed=3, gaits=(0, 6, 1), robot_types=(0, 1, 2))
+        rec = rec.copy()
+        rec[:4, REC_CONTACT:REC_CONTACT + 4 * h] = 1.0          # standing: polish overflow path
+        a = emu.solve(rec, h, params, rt)
+        b = emu.solve(rec, h, params, rt, split=True)
+        assert np.array_equal(a["grf_full"], b["grf_full"]) and np.array_equal(a["status"], b["status"])
+        assert np.array_equal(a["info"], b["info"]) and a["info"][:4, 7].max() > 6 * h
+    seq, _ = _qp_sequence("aliengo_trot")
+    wa, wb = np.zeros((1, 2 + 76 * 10)), np.zeros((1, 2 + 76 * 10))
+    from rl_mpc_locomotion_b200.robots import params_table
+    for t in range(len(seq)):
+        a = emu.solve(seq[t:t + 1], 10, params_table(), None, warm=wa)
+        b = emu.solve(seq[t:t + 1], 10, params_table(), None, warm=wb, split=True)
+        assert np.array_equal(a["grf_full"], b["grf_full"]) and np.array_equal(wa, wb) and np.array_equal(a["info"], b["info"])

@@ -28,15 +28,57 @@ static void run(const float* rec, int n, const float* rp, const int* rt, const m
                         grf_full ? grf_full + (size_t)r * 12 * H : nullptr, &st,
                         nullptr, info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr,
                         dbg ? dbg + (size_t)r * dbg_stride : nullptr,
-                        warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+                        warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr, nullptr);
     if (st == MPC_STATUS_POLISH_OVERFLOW)   // the overflow kernel's job on the device
       mpc::solve_robot<H, true, 12 * H>(rec + (size_t)r * stride, rpr, prm, smb.data(), grf0 + (size_t)r * 12,
                           grf_full ? grf_full + (size_t)r * 12 * H : nullptr, &st,
                           nullptr, info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr,
                           dbg ? dbg + (size_t)r * dbg_stride : nullptr,
-                          warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+                          warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr, nullptr);
     if (status) status[r] = st;
   }
+}
+
+// The phase-split batch path (three kernels on the device): SETUP -> ADMM -> POLISH through the workspace row.
+template <int H>
+static void run_split(const float* rec, int n, const float* rp, const int* rt, const mpc::SolveParams& prm,
+                      float* grf0, float* grf_full, int32_t* status, double* info, double* warm) {
+  using D = mpc::Dims<H>;
+  using DB = mpc::Dims<H, 12 * H>;
+  using WL = mpc::WsLayout<H>;
+  std::vector<double> smb(DB::SMEM_DOUBLES, 0.0), ws(WL::STRIDE, 0.0);
+  mpc::fill_tables<H, 12 * H>(smb.data(), prm.dt);
+  const int stride = MPC_REC_STRIDE(H);
+  for (int r = 0; r < n; ++r) {
+    const float* rpr = rp + (size_t)(rt ? rt[r] : 0) * MPC_ROBOT_PARAMS_STRIDE;
+    const float* rc = rec + (size_t)r * stride;
+    float* g0 = grf0 + (size_t)r * 12;
+    float* gf = grf_full ? grf_full + (size_t)r * 12 * H : nullptr;
+    double* inf = info ? info + (size_t)r * mpc::INFO_STRIDE : nullptr;
+    double* wm = warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr;
+    int32_t st = 0;
+    // every phase runs in a FRESH shared-memory image: nothing but the workspace row crosses a kernel boundary
+    { std::vector<double> sm(D::SMEM_DOUBLES, -7.0); mpc::fill_tables<H>(sm.data(), prm.dt);
+      mpc::solve_robot<H, true, 6 * H, mpc::PH_SETUP>(rc, rpr, prm, sm.data(), g0, gf, &st, nullptr, inf, nullptr, wm, ws.data()); }
+    { std::vector<double> sm(D::SMEM_DOUBLES, -7.0); mpc::fill_tables<H>(sm.data(), prm.dt);
+      mpc::solve_robot<H, true, 6 * H, mpc::PH_ADMM>(rc, rpr, prm, sm.data(), g0, gf, &st, nullptr, inf, nullptr, wm, ws.data()); }
+    if (ws[mpc::WS_STAGE] == mpc::kWsStagePolish) {
+      std::vector<double> sm(D::SMEM_DOUBLES, -7.0); mpc::fill_tables<H>(sm.data(), prm.dt);
+      mpc::solve_robot<H, true, 6 * H, mpc::PH_POLISH>(rc, rpr, prm, sm.data(), g0, gf, &st, nullptr, inf, nullptr, wm, ws.data());
+    }
+    if (st == MPC_STATUS_POLISH_OVERFLOW)
+      mpc::solve_robot<H, true, 12 * H>(rc, rpr, prm, smb.data(), g0, gf, &st, nullptr, inf, nullptr, wm, nullptr);
+    if (status) status[r] = st;
+  }
+}
+
+extern "C" int mpc_emu_solve_split(const float* rec, int n, int horizon, const float* rp, const int* rt,
+                                   const mpc::SolveParams* prm, float* grf0, float* grf_full,
+                                   int32_t* status, double* info, double* warm) {
+  if (horizon == 10) run_split<10>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, warm);
+  else if (horizon == 16) run_split<16>(rec, n, rp, rt, *prm, grf0, grf_full, status, info, warm);
+  else return -1;
+  return 0;
 }
 
 extern "C" int mpc_emu_solve(const float* rec, int n, int horizon, const float* rp, const int* rt,
@@ -104,7 +146,7 @@ extern "C" int mpc_emu_tick(const mpc::SolveParams* prm_in, const mpc::TickParam
       mpc::fill_tables<H>(sm.data(), prm.dt);
       double info[mpc::INFO_STRIDE] = {0};
       mpc::solve_robot<H, true>(rec, rp + (size_t)type * MPC_ROBOT_PARAMS_STRIDE, prm, sm.data(), grf, nullptr, &st_code,
-                          nullptr, info, nullptr, warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr);
+                          nullptr, info, nullptr, warm ? warm + (size_t)r * MPC_WARM_STRIDE(H) : nullptr, nullptr);
       reinterpret_cast<int*>(st)[MPC_ST_ITERS] = (int)info[mpc::INFO_ITERS];
       if (grf0) std::memcpy(grf0 + (size_t)r * 12, grf, sizeof(grf));
     }
