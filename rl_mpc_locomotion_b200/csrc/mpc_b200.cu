@@ -67,11 +67,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef MPC_MIN_CTAS
 #define MPC_MIN_CTAS 6   // resident robots per SM the shared-memory-walk build is tuned for (168 regs: no hot-loop spills)
 #endif
-#ifndef MPC_MIN_CTAS_DENSE
-#define MPC_MIN_CTAS_DENSE 4   // h = 10 with M = Hm^-1 in registers: 120 registers of matrix row per lane
-#endif
+// h = 16: 56 KB of shared memory per robot cap the SM at 4 resident CTAs anyway - ask for no more, so that
+// ptxas may use 255 registers instead of 168
 template <int H>
-constexpr int min_ctas() { return mpc::Dims<H>::DENSE_M ? MPC_MIN_CTAS_DENSE : MPC_MIN_CTAS; }
+constexpr int min_ctas() { return H <= 10 ? MPC_MIN_CTAS : (MPC_MIN_CTAS < 4 ? MPC_MIN_CTAS : 4); }
 
 template <int H, int PCAP = 6 * H>
 struct KernelCfg {

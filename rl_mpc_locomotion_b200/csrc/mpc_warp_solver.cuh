@@ -110,17 +110,6 @@ struct Dims {
   // G_k = F_k^-1 U_k ([NW][GS], GS odd: conflict-free rows) lets ksolve() go from s to g = F^-1 U s
   // in one stage.  Only where the extra 6.2 KB do not cost a resident CTA (h = 10: still 6 per SM).
   static constexpr bool FUSE_G = (H <= 10);
-  // EXPERIMENT, off by default (-DMPC_DENSE_M=1): M = Hm^-1 = W^T W held as one dense row per lane IN
-  // REGISTERS (6h <= lanes, i.e. h = 10), so that the ADMM iteration's wrench-space solve is one balanced
-  // 6h-long dot product per lane against a broadcast vector instead of two triangular walks over shared
-  // memory (see factor() / ksolve()).  Measured on B200 (profiles/r2_experiments.md): the per-iteration
-  // latency of a CTA drops from 4336 to 3079 cycles, but the 120 extra registers cap the SM at 4 resident
-  // robots (255 registers, hot-loop spills) and forming M costs as much as the factorisation itself:
-  // 4.96 ms vs 3.55 ms for the 4096-robot OSQP-faithful solve.  Parity-tested, not shipped.
-#ifndef MPC_DENSE_M
-#define MPC_DENSE_M 0
-#endif
-  static constexpr bool DENSE_M = (MPC_DENSE_M != 0) && (NW <= NL) && (NW % 12 == 0);
   static constexpr int GS = 13;
   static constexpr int OFF_G = OFF_DSM + (NV > 2 * PCAP ? NV : 2 * PCAP);
   static constexpr int SMEM_DOUBLES = OFF_G + (FUSE_G ? NW * GS + (NW * GS & 1) : 0);
@@ -528,7 +517,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
   PER_LANE_ARR(double, xt, [NS][3]);
   PER_LANE(double, red);               // reduction operand
   PER_LANE(double, red2);
-  PER_LANE_ARR(double, mrow, [D::DENSE_M ? NW : 1]);   // row `lane` of M = Hm^-1 (DENSE_M only)
 
   double cscale = 1.0;  // OSQP's cost scaling c
   if constexpr (DO_SETUP) {
@@ -1075,33 +1063,6 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
     WSYNC();
     cholesky(NW);
     invert_lower(NW);
-    if constexpr (D::DENSE_M) {
-      // M = W^T W, row `lane` into registers: M[i][j] = sum_{k >= max(i,j)} W[k][i] W[k][j].  Rows of W
-      // are visited top to bottom in chunks of 12 so that the unrolled j range is a compile-time
-      // constant per chunk; W[k][j] is a broadcast read, W[k][lane] is contiguous across the lanes.
-      LANES_BEGIN
-      if (lane < NW) {
-#pragma unroll
-        for (int j = 0; j < NW; ++j) _(mrow)[j] = 0.0;
-#pragma unroll
-        for (int kb = 0; kb < NW / 12; ++kb) {
-#pragma unroll 1
-          for (int k = 12 * kb; k < 12 * kb + 12; ++k) {
-            if (lane <= k) {
-              const double* const rowk = Wp + tri(k);
-              const double dk = dinv[k];
-              const double wki = (lane == k) ? dk : rowk[lane];
-#pragma unroll
-              for (int j = 0; j < 12 * kb + 12; ++j) {
-                const double wkj = (j < k) ? rowk[j] : (j == k ? dk : 0.0);
-                _(mrow)[j] += wki * wkj;
-              }
-            }
-          }
-        }
-      }
-      LANES_END
-    }
   };
 
   // ksolve(): xt = K^-1 tmp3  (K = Delta + U^T Q U) through the wrench-space system
@@ -1164,73 +1125,53 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       WSYNC();
     MPC_TICK(3);
     }
-    if constexpr (D::DENSE_M) {
-      LANES_BEGIN  // w = M g: one row of M per lane (registers) against the broadcast g
-      if (lane < NW) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-        for (int k = 0; k < NW; k += 4) {
-          const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
-          const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
-          a0 += _(mrow)[k] * g01.x;
-          a1 += _(mrow)[k + 1] * g01.y;
-          a2 += _(mrow)[k + 2] * g23.x;
-          a3 += _(mrow)[k + 3] * g23.y;
-        }
-        vt[lane] = (a0 + a1) + (a2 + a3);
+    LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
+    for (int i = lane; i < NW; i += NL) {
+      const double* rowi = Wp + tri(i);
+      double a0 = dinv[i] * vg[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = 0;
+      for (; k + 3 < i; k += 4) {
+        const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+        const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
+        a0 += rowi[k] * g01.x;
+        a1 += rowi[k + 1] * g01.y;
+        a2 += rowi[k + 2] * g23.x;
+        a3 += rowi[k + 3] * g23.y;
       }
-      LANES_END
-      WSYNC();
-    MPC_TICK(4);
-    } else {
-      LANES_BEGIN  // y = W g   (row walk; rows at the same column hit distinct banks, see tri())
-      for (int i = lane; i < NW; i += NL) {
-        const double* rowi = Wp + tri(i);
-        double a0 = dinv[i] * vg[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 3 < i; k += 4) {
-          const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
-          const double2 g23 = *reinterpret_cast<const double2*>(vg + k + 2);
-          a0 += rowi[k] * g01.x;
-          a1 += rowi[k + 1] * g01.y;
-          a2 += rowi[k + 2] * g23.x;
-          a3 += rowi[k + 3] * g23.y;
-        }
-        if (k < i) {  // last 1..3 columns as one predicated body (no scalar tail loop)
-          const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
-          a0 += rowi[k] * g01.x;
-          if (k + 1 < i) a1 += rowi[k + 1] * g01.y;
-          if (k + 2 < i) a2 += rowi[k + 2] * vg[k + 2];
-        }
-        vw[i] = (a0 + a1) + (a2 + a3);
+      if (k < i) {  // last 1..3 columns as one predicated body (no scalar tail loop)
+        const double2 g01 = *reinterpret_cast<const double2*>(vg + k);
+        a0 += rowi[k] * g01.x;
+        if (k + 1 < i) a1 += rowi[k + 1] * g01.y;
+        if (k + 2 < i) a2 += rowi[k + 2] * vg[k + 2];
       }
-      LANES_END
-      WSYNC();
-    MPC_TICK(5);
-      LANES_BEGIN  // w = W^T y (column walk).  All lanes of a warp visit the SAME row i at the same
-      // time (lanes whose column is not yet below the diagonal are predicated off): W[i][c] is then
-      // contiguous across the lanes (no bank conflicts) and y[i] is a broadcast.  A warp issues its
-      // longest column's trip count anyway, so the uniform loop costs no extra steps.
-      static_assert(NW % 4 == 0, "column walk takes rows four at a time");
-      for (int c = lane; c < NW; c += NL) {
-        double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int i = c & ~31;                       // first column of this warp: a multiple of 4
-        const double* p = Wp + tri(i) + c;     // &W[i][c] (dereferenced only where c < i)
-        for (; i < NW; i += 4) {
-          const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
-          const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
-          if (c < i) a0 += p[0] * y01.x;
-          if (c < i + 1) a1 += p[i + 1] * y01.y;
-          if (c < i + 2) a2 += p[2 * i + 3] * y23.x;
-          if (c < i + 3) a3 += p[3 * i + 6] * y23.y;
-          p += 4 * i + 10;
-        }
-        vt[c] = (a0 + a1) + (a2 + a3);
-      }
-      LANES_END
-      WSYNC();
-    MPC_TICK(6);
+      vw[i] = (a0 + a1) + (a2 + a3);
     }
+    LANES_END
+    WSYNC();
+    MPC_TICK(5);
+    LANES_BEGIN  // w = W^T y (column walk).  All lanes of a warp visit the SAME row i at the same
+    // time (lanes whose column is not yet below the diagonal are predicated off): W[i][c] is then
+    // contiguous across the lanes (no bank conflicts) and y[i] is a broadcast.  A warp issues its
+    // longest column's trip count anyway, so the uniform loop costs no extra steps.
+    static_assert(NW % 4 == 0, "column walk takes rows four at a time");
+    for (int c = lane; c < NW; c += NL) {
+      double a0 = dinv[c] * vw[c], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int i = c & ~31;                       // first column of this warp: a multiple of 4
+      const double* p = Wp + tri(i) + c;     // &W[i][c] (dereferenced only where c < i)
+      for (; i < NW; i += 4) {
+        const double2 y01 = *reinterpret_cast<const double2*>(vw + i);
+        const double2 y23 = *reinterpret_cast<const double2*>(vw + i + 2);
+        if (c < i) a0 += p[0] * y01.x;
+        if (c < i + 1) a1 += p[i + 1] * y01.y;
+        if (c < i + 2) a2 += p[2 * i + 3] * y23.x;
+        if (c < i + 3) a3 += p[3 * i + 6] * y23.y;
+        p += 4 * i + 10;
+      }
+      vt[c] = (a0 + a1) + (a2 + a3);
+    }
+    LANES_END
+    WSYNC();
+    MPC_TICK(6);
     LANES_BEGIN  // v = g - F^-1 w  -> vecB (NW <= NV)
     for (int i = lane; i < NW; i += NL) {
       const int k = i / 6, c = i % 6;
