@@ -801,7 +801,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
       }
       // diagonal entry carries + alpha (P_vv >= 0, so |P_vv + alpha| only grows the max)
       const double pd = 2.0 * (gam[k2 * H + k2] * G1[b * 12 + b] + nnm[k2 * H + k2] * G2[b * 12 + b]) + alpha;
-      vecA[v] = fmax(fmax(m0, m1), Dsm[v] * pd) * Dsm[v];
+      vecA[v] = maxd(maxd(m0, m1), Dsm[v] * pd) * Dsm[v];
     }
     LANES_END
     WSYNC();
@@ -820,7 +820,7 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int s = 0; s < NS; ++s)
           if (_(valid)[s])
     #pragma unroll
-            for (int a = 0; a < 3; ++a) qmax = fmax(qmax, fabs(_(qb)[s][a]));
+            for (int a = 0; a < 3; ++a) qmax = maxd(qmax, fabs(_(qb)[s][a]));
         _(red) = ssum;
         _(red2) = qmax;
         LANES_END
@@ -848,18 +848,18 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
           const double* Dd = _(Dv)[s];
           const double am0 = fabs(mu0), am1 = fabs(mu1), am2 = fabs(mu2), am3 = fabs(mu3);
           double colA[3];
-          colA[0] = fmax(E[0], E[1]) * Dd[0];
-          colA[1] = fmax(E[2], E[3]) * Dd[1];
-          colA[2] = fmax(fmax(fmax(E[0] * am0, E[1] * am1), fmax(E[2] * am2, E[3] * am3)), E[4]) * Dd[2];
+          colA[0] = maxd(E[0], E[1]) * Dd[0];
+          colA[1] = maxd(E[2], E[3]) * Dd[1];
+          colA[2] = maxd(maxd(maxd(E[0] * am0, E[1] * am1), maxd(E[2] * am2, E[3] * am3)), E[4]) * Dd[2];
           double rowA[5];
-          rowA[0] = E[0] * fmax(Dd[0], am0 * Dd[2]);
-          rowA[1] = E[1] * fmax(Dd[0], am1 * Dd[2]);
-          rowA[2] = E[2] * fmax(Dd[1], am2 * Dd[2]);
-          rowA[3] = E[3] * fmax(Dd[1], am3 * Dd[2]);
+          rowA[0] = E[0] * maxd(Dd[0], am0 * Dd[2]);
+          rowA[1] = E[1] * maxd(Dd[0], am1 * Dd[2]);
+          rowA[2] = E[2] * maxd(Dd[1], am2 * Dd[2]);
+          rowA[3] = E[3] * maxd(Dd[1], am3 * Dd[2]);
           rowA[4] = E[4] * Dd[2];
   #pragma unroll
           for (int a = 0; a < 3; ++a) {
-            const double nrm = fmax(cscale * vecA[3 * j + a], colA[a]);
+            const double nrm = maxd(cscale * vecA[3 * j + a], colA[a]);
             const double dtmp = MPC_RSQRT(limit_scaling(nrm));
             _(Dv)[s][a] *= dtmp;
             _(qb)[s][a] *= dtmp;
@@ -1386,25 +1386,25 @@ MPC_FN void solve_robot(const float* rec, const float* rp, const SolveParams& pr
         for (int r = 0; r < 5; ++r) {
           const double ei = 1.0 / _(Ev)[s][r];
           const double rp_ = _(Axv)[s][r] - _(zv)[s][r];
-          _(nrm)[0] = fmax(_(nrm)[0], fabs(ei * rp_));
-          _(nrm)[2] = fmax(_(nrm)[2], fabs(ei * _(zv)[s][r]));
-          _(nrm)[3] = fmax(_(nrm)[3], fabs(ei * _(Axv)[s][r]));
-          _(nrm)[7] = fmax(_(nrm)[7], fabs(rp_));
-          _(nrm)[8] = fmax(_(nrm)[8], fabs(_(zv)[s][r]));
-          _(nrm)[9] = fmax(_(nrm)[9], fabs(_(Axv)[s][r]));
+          _(nrm)[0] = maxd(_(nrm)[0], fabs(ei * rp_));
+          _(nrm)[2] = maxd(_(nrm)[2], fabs(ei * _(zv)[s][r]));
+          _(nrm)[3] = maxd(_(nrm)[3], fabs(ei * _(Axv)[s][r]));
+          _(nrm)[7] = maxd(_(nrm)[7], fabs(rp_));
+          _(nrm)[8] = maxd(_(nrm)[8], fabs(_(zv)[s][r]));
+          _(nrm)[9] = maxd(_(nrm)[9], fabs(_(Axv)[s][r]));
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const double dii = 1.0 / _(Dv)[s][a];
           const double rd = _(qb)[s][a] + _(Pxv)[s][a] + _(Atyv)[s][a];
-          _(nrm)[1] = fmax(_(nrm)[1], fabs(dii * rd));
-          _(nrm)[4] = fmax(_(nrm)[4], fabs(dii * _(qb)[s][a]));
-          _(nrm)[5] = fmax(_(nrm)[5], fabs(dii * _(Atyv)[s][a]));
-          _(nrm)[6] = fmax(_(nrm)[6], fabs(dii * _(Pxv)[s][a]));
-          _(nrm)[10] = fmax(_(nrm)[10], fabs(rd));
-          _(nrm)[11] = fmax(_(nrm)[11], fabs(_(qb)[s][a]));
-          _(nrm)[12] = fmax(_(nrm)[12], fabs(_(Atyv)[s][a]));
-          _(nrm)[13] = fmax(_(nrm)[13], fabs(_(Pxv)[s][a]));
+          _(nrm)[1] = maxd(_(nrm)[1], fabs(dii * rd));
+          _(nrm)[4] = maxd(_(nrm)[4], fabs(dii * _(qb)[s][a]));
+          _(nrm)[5] = maxd(_(nrm)[5], fabs(dii * _(Atyv)[s][a]));
+          _(nrm)[6] = maxd(_(nrm)[6], fabs(dii * _(Pxv)[s][a]));
+          _(nrm)[10] = maxd(_(nrm)[10], fabs(rd));
+          _(nrm)[11] = maxd(_(nrm)[11], fabs(_(qb)[s][a]));
+          _(nrm)[12] = maxd(_(nrm)[12], fabs(_(Atyv)[s][a]));
+          _(nrm)[13] = maxd(_(nrm)[13], fabs(_(Pxv)[s][a]));
         }
       }
     }

@@ -60,7 +60,10 @@ __device__ __forceinline__ void wmaxv(const double (&v)[K], double (&out)[K]) {
   for (int q = 0; q < K; ++q) {
     double t = v[q];
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) t = fmax(t, shfl_xor_d(t, m));
+    for (int m = 16; m > 0; m >>= 1) {   // compare-select instead of fmax (7 instructions): the operands are
+      const double u = shfl_xor_d(t, m);  // running maxima of |.| that started from 0, never NaN
+      t = u > t ? u : t;
+    }
     out[q] = t;
   }
 #if MPC_NL == 64
@@ -71,7 +74,7 @@ __device__ __forceinline__ void wmaxv(const double (&v)[K], double (&out)[K]) {
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < K; ++q) out[q] = fmax(b[q], b[16 + q]);
+  for (int q = 0; q < K; ++q) out[q] = b[16 + q] > b[q] ? b[16 + q] : b[q];
   __syncthreads();
 #endif
 }
