@@ -80,12 +80,15 @@ __device__ __forceinline__ void wmaxv(const double (&v)[K], double (&out)[K]) {
 }
 __device__ __forceinline__ double wmax(double v) {
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v = fmax(v, shfl_xor_d(v, m));
+  for (int m = 16; m > 0; m >>= 1) {
+    const double u = shfl_xor_d(v, m);
+    v = u > v ? u : v;
+  }
 #if MPC_NL == 64
   double* b = xbuf();
   if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
   __syncthreads();
-  v = fmax(b[0], b[1]);
+  v = b[1] > b[0] ? b[1] : b[0];
   __syncthreads();
 #endif
   return v;
