@@ -1,7 +1,7 @@
 """BASELINE config 5: batch sweep 256 -> 65536 robots per GPU x {OSQP-faithful, fixed 25/50/100 ADMM iterations}
 on 1 / 2 / 4 / 8 GPUs (weak scaling: every rank owns its own shard; device time, max over ranks).
 
-  python tools/sweep.py                                   # 1 GPU
+  python tools/sweep.py                                   # 1 GPU   (SWEEP_SIZES=1024,4096,... trims the size list)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sweep.py
 
 Rank 0 prints one JSON document (also written to gpurun_out/sweep_config5_<N>gpu.json)."""
@@ -24,7 +24,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-sizes = [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+sizes = [int(x) for x in os.environ.get("SWEEP_SIZES", "256,512,1024,2048,4096,8192,16384,32768,65536").split(",")]
 modes = [("osqp", {})] + [(f"fixed{k}", dict(mode=_lib.MODE_FIXED, admm_iters=k, polish=0)) for k in (25, 50, 100)]
 rec_all, rt_all, params, _ = synth.make_batch(max(sizes), 10, seed=1000 + rank)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
