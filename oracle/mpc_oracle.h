@@ -10,12 +10,19 @@
  *     /root/reference/extern/osqp into oracle/_ref/libosqp_ref.so (oracle/Makefile),
  *     driven with the reference's exact settings and glue (mpc_osqp.cc:690-796).
  *
- * PARITY STATUS: the reference holds NO golden vectors / tests for this path and
- * mpc_osqp.cc itself cannot be compiled here (Eigen + qpOASES submodules are empty),
- * so the *builder* half of this oracle is "parity unpinned" by the reference; it is
- * instead cross-checked against an independent NumPy/SciPy transcription
- * (oracle/np_builder.py, scipy.linalg.expm) in tests/test_oracle.py.  The *solver*
- * half is the real reference code.
+ * PARITY STATUS: pinned to the reference's own source.  The reference holds no golden
+ * vectors / tests for this path and vendors Eigen, qpOASES and pybind11 as git submodules
+ * whose contents are absent from /root/reference (the image has no Eigen either), so
+ * mpc_osqp.cc cannot be built against its real dependencies here.  It IS built, unmodified
+ * and from where it lies, against oracle/eigen_standin/ (our restatement of the dense Eigen
+ * subset it uses, qpOASES declarations, an empty pybind11/eigen.h) and the unmodified OSQP:
+ * oracle/_ref/refmod/mpc_osqp*.so (oracle/Makefile).  tests/test_reference_source.py holds
+ * this restatement, the golden vectors and the warm-start path to that build (2.5e-8 N on
+ * the bench distributions) and replays the unmodified reference Python through it.  What
+ * remains ours in that build: dense products, the 3x3 inverse, the quaternion formulas and
+ * the Pade matrix exponential underneath the reference's lines.  The builder is further
+ * cross-checked against two independent NumPy/SciPy transcriptions (oracle/np_builder.py,
+ * scipy.linalg.expm) in tests/test_oracle.py.  The *solver* half is the real reference code.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.

@@ -3,7 +3,8 @@
 Drives the reference's own objects (RobotRunnerMin wiring, reference/MPC_Controller/
 robot_runner/RobotRunnerMin.py:54-76) on a simulator-free kinematic replay, with the oracle's
 `mpc_osqp` pybind module (oracle/mpc_osqp*.so: reference OSQP, COLD mode = fresh workspace
-per solve) standing in for the native module that cannot be built here.  Logs, per tick, the
+per solve) standing in for the native module (`--refmod`: the reference's own mpc_osqp.cc compiled
+unmodified against oracle/eigen_standin, OSQP branch).  Logs, per tick, the
 inputs, the StateEstimator.update() outputs, the 13 QP arguments when the MPC fires, and the
 resulting leg torques.  Run in the build container only (needs /root/reference).
 """
@@ -16,6 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 os.environ["MPC_ORACLE_MODE"] = "warm" if "--warm" in sys.argv else "cold"
 sys.path.insert(0, os.path.join(ROOT, "oracle"))   # provides `import mpc_osqp`
+if "--refmod" in sys.argv:   # ... or the reference's OWN mpc_osqp.cc compiled unmodified (oracle/Makefile, eigen_standin):
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref", "refmod"))   # persistent workspace = the warm runs
 sys.path.insert(0, "/root/reference")
 
 import contextlib, io  # noqa: E402
@@ -47,6 +50,12 @@ def run_case(name, robot, gait, flat, ticks, seed, with_weights, compact=False):
     log = {k: [] for k in ("dof", "body", "cmd", "vBody", "omegaBody", "rpyBody", "groundR", "z_pre", "z_post",
                            "normal", "contact_phase", "torques", "f_ff", "counter", "solved", "qp_args", "qp_out")}
     calls = []
+    if "--refmod" in sys.argv:   # the reference's Python asks for mpc.QPOASES (ConvexMPCLocomotion.py:108), whose
+        # source is absent; the north-star path is the OSQP branch of the same file: same constructor arguments
+        import mpc_osqp as _mpc
+        q = runner.data._quadruped
+        runner.cMPC._cpp_mpc = _mpc.ConvexMpc(q._bodyMass, list(q._bodyInertia), 4, runner.cMPC.horizonLength,
+                                              runner.cMPC.dtMPC, Parameters.cmpc_alpha, _mpc.OSQP)
     real = runner.cMPC._cpp_mpc.compute_contact_forces
 
     class Proxy:
@@ -120,6 +129,26 @@ def run_case(name, robot, gait, flat, ticks, seed, with_weights, compact=False):
 
 
 if __name__ == "__main__":
+    if "--check" in sys.argv:   # with --refmod: the committed WARM fixtures (recorded with the oracle module) against
+        # a replay through the unmodified reference Python AND the reference's own C++ source
+        g = np.load(os.path.join(HERE, "tick_golden_aliengo_trot_warm.npz"))
+        r = run_case("aliengo_trot_warm", RobotType.ALIENGO, GaitType.TROT, False, 60, 1, True, compact="return")
+        worst = {k: float(np.abs(np.asarray(r[k], np.float64) - g[k]).max()) for k in ("torques", "qp_out", "qp_args", "f_ff")}
+        print("aliengo_trot_warm", worst)
+        assert worst["qp_args"] < 1e-6 and worst["qp_out"] < 1e-4 and worst["torques"] < 1e-5, worst
+        if "--config1" in sys.argv:
+            g = np.load(os.path.join(HERE, "tick_golden_config1_aliengo_trot_1000.npz"))
+            r = run_case("config1", RobotType.ALIENGO, GaitType.TROT, False, 1000, 11, True, compact="return")
+            sel = r["solved"].astype(bool)
+            worst = {"torques": float(np.abs(r["torques"] - g["torques_warm"]).max()),
+                     "qp_out": float(np.abs(r["qp_out"][sel] - g["qp_out_warm"]).max()),
+                     "qp_args": float(np.abs(r["qp_args"][sel] - g["qp_args"]).max())}
+            e = np.abs(r["qp_out"][sel] - g["qp_out_warm"]).max(1)
+            print("config1 (1000 ticks, warm)", worst, "qp_out error percentiles 50/99:", np.percentile(e, [50, 99]))
+            # the warm-started trajectory carries OSQP's own rounding sensitivity from solve to solve (1e-4..5e-4 N
+            # per near-singular polish, tests/test_oracle.py::test_reference_self_noise_*); fixture stored as float32
+            assert worst["qp_args"] < 1e-5 and worst["qp_out"] < 5e-3 and worst["torques"] < 1e-3, worst
+        sys.exit(0)
     if "--config1" in sys.argv:   # BASELINE config 1: 1 Aliengo, trot, h = 10, 1000 ticks of RobotRunnerMin, twice:
         # with a fresh OSQP workspace per solve (cold: every solve is an independent function of its 13
         # arguments) and with the reference's persistent workspace (warm: what mpc_osqp.cc:757-780 does)

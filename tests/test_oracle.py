@@ -1,6 +1,6 @@
-"""CPU tests of the checker itself: the oracle's builder restatement is pinned by two
-independent NumPy/SciPy transcriptions (the reference has no tests for this path and
-mpc_osqp.cc cannot be compiled here, see oracle/mpc_oracle.h), its solver is the real
+"""CPU tests of the checker itself: the oracle's builder restatement against two independent
+NumPy/SciPy transcriptions (the reference has no tests for this path; the pin to the reference's own
+mpc_osqp.cc compiled unmodified is tests/test_reference_source.py), its solver is the real
 reference OSQP, and the committed golden vectors pin both against drift."""
 import os
 
