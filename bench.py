@@ -416,57 +416,66 @@ def main():
     # returns nor the true minimiser, so the error is printed next to the rate.
     fixed = None
     if kind == "qp" and args.mode == "osqp" and not args.no_side and rank == 0:
-        fixed = []
-        for k in (25, 50, 100):
-            mf = BatchedConvexMpc(h, device=dev, robot_params=params, mode=_lib.MODE_FIXED, admm_iters=k, polish=0)
-            for _ in range(3):
-                mf.solve(d_rec, d_rt, out=d_out)
-            torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(5):
-                mf.solve(d_rec, d_rt, out=d_out)
-            f1.record()
-            torch.cuda.synchronize()
-            row = {"admm_iters": k, "ms_per_step": f0.elapsed_time(f1) / 5,
-                   "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3), "unit": "solves/s"}
-            if not args.no_cpu_baseline:
-                from oracle import oracle
-                ns = min(64, n_per_gpu)
-                if k == 25:
-                    ref0 = oracle.solve_records(rec[:ns], h, params, rt[:ns], mode=oracle.COLD)[0]
-                    tru0 = oracle.solve_records(rec[:ns], h, params, rt[:ns], mode=oracle.TRUE)[0]
-                f = d_out[:ns].cpu().numpy()
-                e_ref, e_tru = np.abs(f - ref0).max(1), np.abs(f - tru0).max(1)
-                row["grf_err_N"] = {"vs_reference_osqp": {"median": float(np.median(e_ref)), "max": float(e_ref.max())},
-                                    "vs_true_minimiser": {"median": float(np.median(e_tru)), "max": float(e_tru.max())},
-                                    "sample": f"first {ns} robots of this batch, horizon-0 forces, oracle on the host"}
-            fixed.append(row)
-        fixed = {"rows": fixed, "note": "fixed K ADMM iterations, no termination test / rho adaptation / polish; side "
-                                        "measurement on rank 0.  NOT the reference's answer: see grf_err_N"}
+        try:   # a side measurement must never cost the headline line
+            fixed = []
+            # (K, settings on top of the reference's): the reference's rho = 0.1 with Ruiz scaling, and - last row - the
+            # regime in which a fixed budget actually converges (rho = 1e-4, no scaling)
+            for k, extra in ((25, {}), (50, {}), (100, {}), (100, {"rho": 1e-4, "scaling_iters": 0})):
+                mf = BatchedConvexMpc(h, device=dev, robot_params=params, mode=_lib.MODE_FIXED, admm_iters=k, polish=0, **extra)
+                for _ in range(3):
+                    mf.solve(d_rec, d_rt, out=d_out)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(5):
+                    mf.solve(d_rec, d_rt, out=d_out)
+                f1.record()
+                torch.cuda.synchronize()
+                row = {"admm_iters": k, "settings": extra or "reference (rho 0.1, 10 Ruiz passes)",
+                       "ms_per_step": f0.elapsed_time(f1) / 5,
+                       "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3), "unit": "solves/s"}
+                if not args.no_cpu_baseline:
+                    from oracle import oracle
+                    ns = min(64, n_per_gpu)
+                    if not fixed:
+                        ref0 = oracle.solve_records(rec[:ns], h, params, rt[:ns], mode=oracle.COLD)[0]
+                        tru0 = oracle.solve_records(rec[:ns], h, params, rt[:ns], mode=oracle.TRUE)[0]
+                    f = d_out[:ns].cpu().numpy()
+                    e_ref, e_tru = np.abs(f - ref0).max(1), np.abs(f - tru0).max(1)
+                    row["grf_err_N"] = {"vs_reference_osqp": {"median": float(np.median(e_ref)), "max": float(e_ref.max())},
+                                        "vs_true_minimiser": {"median": float(np.median(e_tru)), "max": float(e_tru.max())},
+                                        "sample": f"first {ns} robots of this batch, horizon-0 forces, oracle on the host"}
+                fixed.append(row)
+            fixed = {"rows": fixed, "note": "fixed K ADMM iterations, no termination test / rho adaptation / polish; side "
+                                            "measurement on rank 0.  NOT the reference's answer: see grf_err_N"}
+        except Exception as exc:  # noqa: BLE001
+            fixed = {"error": repr(exc)}
 
     # ---- side measurement: the headline solve again, launched longest-first using the iteration
     # counts of a previous solve of the same robots (the d_order scheduling hint; identical results).
     lpt = None
     if kind == "qp" and args.mode == "osqp" and not args.no_side and rank == 0:
-        from rl_mpc_locomotion_b200.batched import lpt_order
-        info = mpc.solve(d_rec, d_rt, info=True)["info"]
-        order = lpt_order(info)
-        for _ in range(3):
-            mpc.solve(d_rec, d_rt, out=d_out, order=order)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(5):
-            mpc.solve(d_rec, d_rt, out=d_out, order=order)
-        f1.record()
-        torch.cuda.synchronize()
-        it = info[:, 0].cpu().numpy()
-        lpt = {"ms_per_step": f0.elapsed_time(f1) / 5, "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3),
-               "unit": "solves/s", "osqp_iterations": {"mean": float(it.mean()), "median": float(np.median(it)),
-                                                       "max": float(it.max())},
-               "note": "same OSQP-faithful solve, CTAs launched in descending order of the previous solve's "
-                       "iteration counts (perfect prediction here because the batch repeats; side measurement, rank 0)"}
+        try:
+            from rl_mpc_locomotion_b200.batched import lpt_order
+            info = mpc.solve(d_rec, d_rt, info=True)["info"]
+            order = lpt_order(info)
+            for _ in range(3):
+                mpc.solve(d_rec, d_rt, out=d_out, order=order)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(5):
+                mpc.solve(d_rec, d_rt, out=d_out, order=order)
+            f1.record()
+            torch.cuda.synchronize()
+            it = info[:, 0].cpu().numpy()
+            lpt = {"ms_per_step": f0.elapsed_time(f1) / 5, "value_per_gpu": n_per_gpu * 5 / (f0.elapsed_time(f1) * 1e-3),
+                   "unit": "solves/s", "osqp_iterations": {"mean": float(it.mean()), "median": float(np.median(it)),
+                                                           "max": float(it.max())},
+                   "note": "same OSQP-faithful solve, CTAs launched in descending order of the previous solve's "
+                           "iteration counts (perfect prediction here because the batch repeats; side measurement, rank 0)"}
+        except Exception as exc:  # noqa: BLE001
+            lpt = {"error": repr(exc)}
 
     # ---- e2e: the public entry point fed from pinned HOST buffers, copies inside the timed region
     e2e_steps = max(3, min(args.steps, 10))
