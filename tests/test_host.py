@@ -117,3 +117,28 @@ def test_no_reference_gait_can_overflow_the_tick_kernels_polish_buffer():
             for k in range(10):
                 table = gait.mpc_table(gid, k + 0.5, h)
                 assert table.sum() <= 2 * h, (h, gid, k, table.sum())
+
+
+def test_integration_doc_ctypes_stub_matches_the_abi():
+    """INTEGRATION.md §2 shows the ctypes binding a maintainer would write: its settings structure must be the
+    one the package binds (same fields, order and types) and its call must pass every argument of the header."""
+    import ctypes as C
+    import re
+    from rl_mpc_locomotion_b200 import _lib
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    block = re.search(r"class MpcB200Settings\(C\.Structure\):.*?\n\n", doc, re.S).group(0)
+    ns = {"C": C}
+    exec(block, ns)
+    got = [(n, t) for n, t in ns["MpcB200Settings"]._fields_]
+    want = [(n, t) for n, t in _lib.Settings._fields_]
+    assert [n for n, _ in got] == [n for n, _ in want]
+    assert all(C.sizeof(a) == C.sizeof(b) for (_, a), (_, b) in zip(got, want))
+    assert C.sizeof(ns["MpcB200Settings"]) == C.sizeof(_lib.Settings)
+    call = re.search(r"lib\.mpc_b200_solve_batch\((.*?)\)\nassert", doc, re.S).group(1)
+    call = re.sub(r"#[^\n]*", "", call)                           # drop the trailing comments
+    depth, n_args = 0, 1
+    for ch in call:
+        depth += ch in "([" 
+        depth -= ch in ")]"
+        n_args += (ch == "," and depth == 0)
+    assert n_args == 14                                            # include/mpc_b200.h: mpc_b200_solve_batch
