@@ -189,32 +189,44 @@ def test_fixed_budget_converging_regime(oracle_mod):
     assert np.median(tuned) < 1e-2 * np.median(e_ref) and np.median(stock) > 50.0
 
 
-def _full_size_chunk(lo):
+_FULL_SIZE = {   # bench.py workloads at their full per-GPU size (seed 1000 = bench.py's rank 0)
+    "aliengo_trot_h10_n4096": dict(n=4096, h=10, seed=1000, gaits=(0,), robots=(0,)),
+    "aliengo_mixed_gaits_h10_n2048": dict(n=2048, h=10, seed=1000, gaits=(0, 6, 1), robots=(0,)),
+    "mixed_robots_h16_n2048": dict(n=2048, h=16, seed=1000, gaits=(0, 6, 1), robots=(0, 1, 2)),
+}
+
+
+def _full_size_chunk(job):
     from oracle import oracle
     from rl_mpc_locomotion_b200 import synth
-    rec, rt, params, _ = synth.make_batch(4096, 10, seed=0)          # bench.py's config-2 batch (rank 0)
+    name, lo = job
+    c = _FULL_SIZE[name]
+    rec, rt, params, _ = synth.make_batch(c["n"], c["h"], seed=c["seed"], gaits=c["gaits"], robot_types=c["robots"])
     sl = slice(lo, lo + 256)
-    out = emu.solve(rec[sl], 10, params, rt[sl])
-    _, ref_full, st = oracle.solve_records(rec[sl], 10, params, rt[sl], mode=oracle.COLD, full=True)
+    out = emu.solve(rec[sl], c["h"], params, rt[sl])
+    _, ref_full, st = oracle.solve_records(rec[sl], c["h"], params, rt[sl], mode=oracle.COLD, full=True)
     return out["grf_full"], out["status"], out["info"][:, 0], ref_full, st
 
 
-def test_full_size_bench_batch_matches_reference_osqp(oracle_mod):
-    """BASELINE config 2 AT ITS FULL SIZE on the CPU: all 4096 QPs of the bench batch through the kernel's lane
-    program (warp emulation) against the reference OSQP - statuses identical, horizon-0 forces (what the
-    controller applies) < 1e-3 N on every robot, full-horizon forces < 1e-3 N at the 99.5th percentile and
-    < 5e-3 N worst (the bar of tests/test_gpu_parity.py; the worst cases are the reference's own near-singular
-    polishes).  The iteration-count distribution is the one DESIGN.md §7b quotes for the tail."""
+@pytest.mark.parametrize("name", list(_FULL_SIZE))
+def test_full_size_bench_batch_matches_reference_osqp(oracle_mod, name):
+    """BASELINE configs 2, 3 (QP part) and 4 AT THEIR FULL PER-GPU SIZE on the CPU: every QP of the bench batch
+    through the kernel's lane program (warp emulation) against the reference OSQP - statuses identical, horizon-0
+    forces (what the controller applies) < 1e-3 N on every robot, full-horizon forces < 1e-3 N at the 99.5th
+    percentile and < 5e-3 N worst (the bar of tests/test_gpu_parity.py; the worst cases are the reference's own
+    near-singular polishes).  For config 2 the iteration-count distribution is the one DESIGN.md §7b quotes."""
     import os as _os
     from concurrent.futures import ProcessPoolExecutor
     emu.lib()
+    n = _FULL_SIZE[name]["n"]
     with ProcessPoolExecutor(min(8, _os.cpu_count() or 1)) as ex:
-        res = list(ex.map(_full_size_chunk, range(0, 4096, 256)))
+        res = list(ex.map(_full_size_chunk, [(name, lo) for lo in range(0, n, 256)]))
     f, st, it, ref, st_ref = (np.concatenate([r[k] for r in res]) for k in range(5))
     assert np.array_equal(st, st_ref) and (st == 1).all()
     e_full, e0 = np.abs(f - ref).max(1), np.abs(f[:, :12] - ref[:, :12]).max(1)
-    print(f"4096 QPs: horizon-0 max {e0.max():.3g} N; full horizon max {e_full.max():.3g} N, 99.5th pct "
+    print(f"{name}: {n} QPs: horizon-0 max {e0.max():.3g} N; full horizon max {e_full.max():.3g} N, 99.5th pct "
           f"{np.percentile(e_full, 99.5):.3g} N; iterations mean {it.mean():.1f} max {it.max():.0f}")
     assert e0.max() < 1e-3 and np.percentile(e_full, 99.5) < 1e-3 and e_full.max() < 5e-3
-    counts = dict(zip(*np.unique(it.astype(int), return_counts=True)))
-    assert counts[75] > counts[50] and it.max() == 350 and 100 < it.mean() < 110
+    if name == "aliengo_trot_h10_n4096":
+        counts = dict(zip(*np.unique(it.astype(int), return_counts=True)))
+        assert counts[75] > counts[50] and it.max() >= 250 and 95 < it.mean() < 115   # bench line: mean 103.4, max 275
