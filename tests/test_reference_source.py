@@ -76,7 +76,7 @@ def test_golden_vectors_match_the_reference_source_build(refmod, h):
     assert err.max() < 2e-4 and np.percentile(err, 90) < 1e-6
 
 
-@pytest.mark.parametrize("name,rtype", [("aliengo_trot", 0), ("a1_bound", 1)])
+@pytest.mark.parametrize("name,rtype", [("aliengo_trot", 0), ("a1_bound", 1), ("aliengo_walk_flat", 0), ("go1_trot_flat", 2)])
 def test_warm_workspace_path_matches_the_reference_source_build(refmod, oracle_mod, name, rtype):
     """ONE persistent `ConvexMpc` over 30 consecutive MPC solves of a replayed gait: the reference's
     osqp_update_P_A / update_lin_cost / update_bounds / warm-started osqp_solve path (mpc_osqp.cc:760-780)
